@@ -1,0 +1,165 @@
+/*
+ * qls_abi.h -- C ABI of the B200 statevector engine (libqls_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of SURFQuantum/qc-quantum-linear-systems:
+ * applying a gate stream to a complex statevector and reducing the result.  In the reference
+ * that path is reached through Python objects of third-party packages, so each entry point
+ * cites the reference call site (path relative to the reference tree) whose work it performs:
+ *
+ *   Statevector(hhl_circuit).data      quantum_linear_systems/implementations/hhl_qiskit_implementation.py:49
+ *   Statevector(res.state).data        quantum_linear_systems/implementations/vqls_qiskit_implementation.py:65
+ *   HHL.solve -> _calculate_norm       quantum_linear_systems/implementations/hhl_qiskit_implementation.py:35-38,54
+ *   estimator.run(...).result().values quantum_linear_systems/implementations/vqls_qiskit_implementation.py:55-62
+ *   extract_hhl_solution_vector_...    quantum_linear_systems/utils.py:77-94
+ *
+ * Conventions: plain pointers and sizes only.  `state`, `scratch`, `workspace`, `*_dev` are
+ * DEVICE pointers owned by the caller (the Python host allocates them as torch tensors);
+ * `*_host` are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Amplitude index bit q = qubit q (little endian).  dtype: QLS_C128 = interleaved
+ * (re, im) doubles, QLS_C64 = interleaved floats.  Every function returns QLS_OK (0) or an error
+ * code; qls_last_error() gives the text for the calling thread.  Calls are asynchronous on
+ * `stream` unless stated otherwise.
+ */
+#ifndef QLS_ABI_H
+#define QLS_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLS_ABI_VERSION 1
+
+enum { QLS_C128 = 0, QLS_C64 = 1 };
+enum { QLS_OK = 0, QLS_ERR_ARG = 1, QLS_ERR_CUDA = 2, QLS_ERR_UNSUPPORTED = 3, QLS_ERR_NOMEM = 4 };
+
+/* ---- fused-block program ------------------------------------------------------------------ */
+
+enum {
+  QLS_OP_DENSE = 1, /* 2^k x 2^k complex matrix on k tile qubits (k <= 5), optional controls   */
+  QLS_OP_DIAG = 2,  /* merged diagonal run: amp *= table[index bits]                          */
+  QLS_OP_MUXRY = 3  /* uniformly controlled RY: (cos, sin) table selected by index bits       */
+};
+
+#define QLS_MAX_SEG 6
+#define QLS_MAX_HIGH 8
+#define QLS_MAX_FSEG 16
+#define QLS_OP_FLAG_REAL 1u  /* DENSE matrix is real (imaginary parts are zero) */
+#define QLS_OP_FLAG_PARAM 2u /* batch kernel only: a k=1 RY whose angle comes from the parameter array */
+
+/* bit-field gather: ((x >> src) & ((1 << width) - 1)) << dst */
+typedef struct QlsSeg {
+  uint8_t src, width, dst, pad;
+} QlsSeg;
+
+/* One operation applied to a shared-memory tile of 2^tile_bits amplitudes. 128 bytes. */
+typedef struct QlsOp {
+  int32_t kind;       /* QLS_OP_*                                                             */
+  int32_t k;          /* DENSE: number of target qubits; MUXRY: 1; DIAG: unused               */
+  uint8_t tq[8];      /* tile-local bit positions of the targets, ascending; matrix bit j <-> tq[j] */
+  uint32_t lc_mask;   /* controls that are tile qubits: (local_index & lc_mask) == lc_val     */
+  uint32_t lc_val;
+  uint64_t xc_mask;   /* controls outside the tile, tested on the tile's global base index    */
+  uint64_t xc_val;
+  uint64_t pool_off;  /* byte offset of the matrix / table in the constant pool               */
+  uint8_t n_lseg;     /* DIAG/MUXRY: table index fields taken from the tile-local index       */
+  uint8_t n_xseg;     /*             ... and from the tile's global base index                */
+  uint8_t flags;
+  uint8_t pad0;
+  uint32_t pad1;
+  QlsSeg lseg[QLS_MAX_SEG];
+  QlsSeg xseg[QLS_MAX_SEG];
+  uint32_t param_index; /* batch kernel: angle = params[circuit][param_index] when QLS_OP_FLAG_PARAM */
+  float param_coeff;    /*               angle = coeff * param + offset                              */
+  float param_offset;
+  uint8_t reserved[12];
+} QlsOp;
+
+/* One pass over the state: every tile (2^tile_bits amplitudes: the low `low_bits` qubits plus
+ * `n_high` further qubits) is staged in shared memory, ops [op_begin, op_begin+op_count) are
+ * applied, and the tile is written back: one HBM read + one write per touched amplitude. */
+typedef struct QlsPass {
+  int32_t tile_bits;
+  int32_t low_bits;
+  int32_t n_high;
+  uint8_t high[QLS_MAX_HIGH]; /* qubit positions of tile-local bits low_bits.., ascending     */
+  uint32_t op_begin;
+  uint32_t op_count;
+  uint64_t fix_mask;          /* pass-level controls (LOCAL index bits outside the tile):     */
+  uint64_t fix_val;           /* tiles with (index & fix_mask) != fix_val are not touched     */
+  int32_t n_fseg;             /* deposit of the tile counter into the free index bits         */
+  QlsSeg fseg[QLS_MAX_FSEG];
+  uint32_t pad;
+} QlsPass;
+
+typedef struct QlsProgram QlsProgram; /* opaque: device copies of ops + constant pool */
+
+int qls_abi_version(void);
+const char* qls_last_error(void);
+/* sm count, opt-in shared memory per block, total/free device memory of `device` */
+int qls_device_info(int device, int* sm_count, uint64_t* smem_optin, uint64_t* mem_total, uint64_t* mem_free);
+
+/* Upload a lowered program (passes/ops/pool are HOST arrays; pool entries are in `dtype`).
+ * Synchronous.  Replaces the per-gate loop of Statevector._evolve_instruction [hhl..:49]. */
+int qls_program_create(const QlsPass* passes_host, uint32_t n_passes, const QlsOp* ops_host, uint32_t n_ops,
+                       const void* pool_host, uint64_t pool_bytes, int dtype, int device, QlsProgram** out);
+int qls_program_destroy(QlsProgram* prog);
+/* Run passes [pass_begin, pass_end) on a state of 2^n_local amplitudes.  `index_offset` is the
+ * global index of local amplitude 0 (rank << n_local for a sharded state, else 0). */
+int qls_program_run(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset, uint32_t pass_begin,
+                    uint32_t pass_end, void* stream);
+
+/* ---- state initialisation and host <-> device access ------------------------------------- */
+
+/* psi = 0; psi[basis_index] = 1 (pass UINT64_MAX to only zero).  [Statevector.from_instruction] */
+int qls_sv_init_basis(void* state, int n_local, int dtype, uint64_t basis_index, void* stream);
+/* copy `count` amplitudes host -> state[offset..) / state[offset..) -> host (same dtype);
+ * synchronous with respect to the host buffer.  [state preparation a7 / `.data` hhl..:49] */
+int qls_sv_write(void* state, int dtype, uint64_t offset, const void* amps_host, uint64_t count, void* stream);
+int qls_sv_read(const void* state, int dtype, uint64_t offset, void* amps_host, uint64_t count, void* stream);
+/* psi *= (re + i*im)  -- a definition's global phase */
+int qls_sv_scale(void* state, int n_local, int dtype, double re, double im, void* stream);
+
+/* ---- reductions (synchronous: result lands in out_host) ----------------------------------- */
+
+enum {
+  QLS_RED_NORM_RANGE = 0, /* a = offset, b = count : sum |psi_i|^2 over the range  [HHL._calculate_norm, utils.py:94] */
+  QLS_RED_PROB_MASK = 1,  /* a = mask,  b = value : sum |psi_i|^2 over ((index_offset|i) & mask) == value          */
+  QLS_RED_EXPECT_Z = 2,   /* a = qubit            : sum (-1)^{bit_a} |psi_i|^2   [Statevector.expectation_value]   */
+  QLS_RED_INNER = 3       /* <other|psi> -> out[0] + i*out[1]  (fidelity)                                            */
+};
+#define QLS_REDUCE_WORKSPACE_BYTES (64u * 1024u)
+int qls_reduce(const void* state, int n_local, int dtype, int kind, uint64_t a, uint64_t b, uint64_t index_offset,
+               const void* other, void* workspace, double* out_host /* [2] */, void* stream);
+
+/* ---- dense controlled-e^{iAt} block as a complex GEMM on the FP64 tensor pipe -------------- */
+
+/* rows of psi.reshape(-1, 2^nb) whose global row index satisfies (row_index & ctrl_mask) ==
+ * ctrl_val are replaced by row @ U^T (U row-major 2^nb x 2^nb, device, in `dtype`).  `scratch`
+ * must hold as many amplitudes as there are selected rows * 2^nb.  [PhaseEstimation's
+ * controlled-U^(2^j) blocks inside HHL.construct_circuit, hhl..:35-38] */
+int qls_ctrl_gemm(void* state, void* scratch, int n_local, int dtype, int nb, uint64_t ctrl_mask, uint64_t ctrl_val,
+                  uint64_t index_offset, const void* u_dev, void* stream);
+
+/* ---- batch of small circuits (VQLS Hadamard tests) ----------------------------------------- */
+
+/* K circuits of n_qubits (<= 12) sharing one op program; ops flagged as parameterised take their
+ * angle from params_dev[circuit*P + index].  out_dev[circuit] = <Z_qubit>.
+ * [Estimator.run(circuits, observables, parameter_values), vqls..:55-62] */
+int qls_batch_expect_z(const QlsProgram* prog, uint32_t pass_index, int n_qubits, int z_qubit, const double* params_dev,
+                       uint32_t n_circuits, uint32_t n_params, double* out_dev, void* stream);
+
+/* ---- global-qubit remap helpers (sharded states) -------------------------------------------- */
+
+/* Gather / scatter the half-open slab of amplitudes whose local bit `qubit` equals `bit_value`
+ * into / from a contiguous buffer (count = 2^(n_local-1)); used to stage NCCL send/recv. */
+int qls_pack_bit(const void* state, void* buffer, int n_local, int dtype, int qubit, int bit_value, uint64_t chunk_begin,
+                 uint64_t chunk_count, void* stream);
+int qls_unpack_bit(void* state, const void* buffer, int n_local, int dtype, int qubit, int bit_value, uint64_t chunk_begin,
+                   uint64_t chunk_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLS_ABI_H */

@@ -346,6 +346,28 @@ class UCRYGate(Gate):
         return UCRYGate(-self.angles)
 
 
+class DiagonalGate(Gate):
+    """Diagonal unitary given by its ``2**k`` diagonal entries (qiskit ``DiagonalGate``)."""
+
+    def __init__(self, diag: Sequence[complex]):
+        d = np.asarray(diag, dtype=complex).reshape(-1)
+        nq = int(round(math.log2(len(d))))
+        if 2**nq != len(d):
+            raise ValueError("diagonal needs 2**k entries")
+        super().__init__("diagonal", nq, [d])
+        self.diag = d
+
+    def to_matrix(self) -> Optional[np.ndarray]:
+        if self._matrix is None:
+            if self.num_qubits > 12:
+                return None
+            self._matrix = np.diag(self.diag)
+        return self._matrix
+
+    def inverse(self) -> "Gate":
+        return DiagonalGate(self.diag.conj())
+
+
 class StatePreparation(Gate):
     """Isometry ``|0...0> -> sum_i amps[i] |i>`` (qiskit ``isometry`` / ``prepare_state``).
 
@@ -475,13 +497,7 @@ class QuantumCircuit:
         return self.append(Gate("unitary", len(qubits), [], m, None, label), qubits)
 
     def diagonal(self, diag: Sequence[complex], qubits: Sequence[int]) -> "QuantumCircuit":
-        d = np.asarray(diag, dtype=complex).reshape(-1)
-        if len(d) != 2 ** len(qubits):
-            raise ValueError("diagonal length does not match qubit count")
-        g = Gate("diagonal", len(qubits), [d], None)
-        g._matrix = None
-        g.diag = d  # type: ignore[attr-defined]
-        return self.append(g, qubits)
+        return self.append(DiagonalGate(diag), qubits)
 
     def ucry(self, angles: Sequence[float], controls: Sequence[int], target: int) -> "QuantumCircuit":
         return self.append(UCRYGate(angles), [target] + list(controls))
@@ -700,8 +716,8 @@ def _leaf_of(op: Gate, qubits: Tuple[int, ...]) -> Optional[Leaf]:
             m = base.to_matrix()
             return None if m is None else Leaf("dense", qubits, m, controls, ctrl_state, base.name)
         return Leaf("init", qubits, base.amplitudes, (), 0, base.name)
-    if base.name == "diagonal":
-        return Leaf("diag", qubits, np.asarray(base.diag, dtype=complex), controls, ctrl_state, "diagonal")
+    if isinstance(base, DiagonalGate):
+        return Leaf("diag", qubits, base.diag, controls, ctrl_state, "diagonal")
     m = base.to_matrix()
     if m is None:
         return None

@@ -1,0 +1,94 @@
+// Shared device/host helpers for libqls_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "qls_abi.h"
+
+static_assert(sizeof(QlsOp) == 128, "QlsOp must be 128 bytes (mirrored in _abi.py)");
+static_assert(sizeof(QlsPass) == 120, "QlsPass must be 120 bytes (mirrored in _abi.py)");
+
+void qls_set_error(const char* fmt, ...);
+
+#define QLS_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      qls_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));     \
+      return QLS_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define QLS_ARG(cond, ...)            \
+  do {                                \
+    if (!(cond)) {                    \
+      qls_set_error(__VA_ARGS__);     \
+      return QLS_ERR_ARG;             \
+    }                                 \
+  } while (0)
+
+struct QlsProgram {
+  int device;
+  int dtype;
+  uint32_t n_passes, n_ops;
+  QlsPass* passes_host;  // host copy (launch geometry is computed on the host)
+  QlsOp* ops_dev;
+  unsigned char* pool_dev;
+  uint64_t pool_bytes;
+};
+
+// ---- complex arithmetic on double2 / float2 -----------------------------------------------------
+template <typename R>
+struct Vec2;
+template <>
+struct Vec2<double> {
+  using type = double2;
+};
+template <>
+struct Vec2<float> {
+  using type = float2;
+};
+
+template <typename V>
+__device__ __forceinline__ V cmul(V a, V b) {
+  V r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  return r;
+}
+// acc += a * b
+template <typename V>
+__device__ __forceinline__ void cfma(V& acc, V a, V b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+__device__ __forceinline__ uint32_t insert_zero_bit(uint32_t x, uint32_t pos) {
+  uint32_t low = x & ((1u << pos) - 1u);
+  return ((x >> pos) << (pos + 1)) | low;
+}
+
+__device__ __forceinline__ uint64_t gather_segs64(uint64_t x, const QlsSeg* s, int n) {
+  uint64_t r = 0;
+  for (int i = 0; i < n; ++i) r |= ((x >> s[i].src) & ((1ull << s[i].width) - 1ull)) << s[i].dst;
+  return r;
+}
+__device__ __forceinline__ uint32_t gather_segs32(uint32_t x, const QlsSeg* s, int n) {
+  uint32_t r = 0;
+  for (int i = 0; i < n; ++i) r |= ((x >> s[i].src) & ((1u << s[i].width) - 1u)) << s[i].dst;
+  return r;
+}
+
+// 16-byte async copy global -> shared (LDGSTS), bypassing L1
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}

@@ -1,0 +1,49 @@
+// Staging kernels for global-qubit remaps of a sharded statevector: the amplitudes whose local bit
+// `qubit` equals `bit_value` are gathered into / scattered from a contiguous buffer that is then
+// exchanged with the partner rank (NCCL send/recv or a peer-memory copy over NVLink).
+#include "qls_common.cuh"
+
+// element j of the slab (j in [0, 2^(n-1))) sits at insert_bit(j, qubit, bit_value) in the state
+template <typename V, bool PACK>
+__global__ void __launch_bounds__(256) qls_pack_bit_kernel(V* __restrict__ state, V* __restrict__ buffer, int qubit,
+                                                            uint64_t bit, uint64_t begin, uint64_t count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t lowmask = (1ull << qubit) - 1ull;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+    const uint64_t j = begin + t;
+    const uint64_t i = ((j >> qubit) << (qubit + 1)) | (bit << qubit) | (j & lowmask);
+    if (PACK) buffer[t] = state[i];
+    else state[i] = buffer[t];
+  }
+}
+
+template <bool PACK>
+static int pack_impl(void* state, void* buffer, int n_local, int dtype, int qubit, int bit_value, uint64_t begin,
+                     uint64_t count, void* stream) {
+  QLS_ARG(state && buffer, "null pointer");
+  QLS_ARG(qubit >= 0 && qubit < n_local, "qubit %d outside the local register of %d", qubit, n_local);
+  QLS_ARG(begin + count <= (1ull << (n_local - 1)), "chunk outside the slab");
+  if (count == 0) return QLS_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint64_t want = (count + 255) / 256;
+  unsigned grid = (unsigned)(want > 148ull * 16 ? 148 * 16 : want);
+  if (dtype == QLS_C128)
+    qls_pack_bit_kernel<double2, PACK><<<grid, 256, 0, s>>>(reinterpret_cast<double2*>(state),
+                                                            reinterpret_cast<double2*>(buffer), qubit,
+                                                            (uint64_t)(bit_value & 1), begin, count);
+  else
+    qls_pack_bit_kernel<float2, PACK><<<grid, 256, 0, s>>>(reinterpret_cast<float2*>(state),
+                                                           reinterpret_cast<float2*>(buffer), qubit,
+                                                           (uint64_t)(bit_value & 1), begin, count);
+  QLS_CUDA(cudaGetLastError());
+  return QLS_OK;
+}
+
+extern "C" int qls_pack_bit(const void* state, void* buffer, int n_local, int dtype, int qubit, int bit_value,
+                            uint64_t chunk_begin, uint64_t chunk_count, void* stream) {
+  return pack_impl<true>(const_cast<void*>(state), buffer, n_local, dtype, qubit, bit_value, chunk_begin, chunk_count, stream);
+}
+extern "C" int qls_unpack_bit(void* state, const void* buffer, int n_local, int dtype, int qubit, int bit_value,
+                              uint64_t chunk_begin, uint64_t chunk_count, void* stream) {
+  return pack_impl<false>(state, const_cast<void*>(buffer), n_local, dtype, qubit, bit_value, chunk_begin, chunk_count, stream);
+}

@@ -1,0 +1,167 @@
+// In-shared-memory application of fused blocks to one tile of 2^T amplitudes.
+// Shared by the streaming tile-pass kernel (tile_pass.cu) and the batched small-circuit kernel
+// (batch_sv.cu), where the "tile" is the whole statevector of one circuit.
+#pragma once
+#include "qls_common.cuh"
+
+// ---- DENSE: 2^K x 2^K matrix on K tile-local qubits ----------------------------------------------
+// One work item = (group of 2^K amplitudes, slice of R = 2^K / S output rows).  Inputs are streamed
+// from shared memory, the R accumulators live in registers, outputs are written once all reads of
+// the group are done (S > 1 needs a block barrier for that; S == 1 does not).
+template <typename V, int K, int S, int THREADS, bool REAL>
+__device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ M, int tid) {
+  constexpr int D = 1 << K;
+  constexpr int R = D / S;
+  const int gbits = T - K;
+  const int nitems = (1 << gbits) * S;
+  uint32_t bit[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) bit[j] = 1u << op.tq[j];
+  const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+
+  for (int it0 = 0; it0 < nitems; it0 += THREADS) {
+    const int item = it0 + tid;
+    bool active = item < nitems;
+    uint32_t idx = 0;
+    int h = 0;
+    V acc[R];
+    if (active) {
+      h = item >> gbits;
+      idx = item & ((1 << gbits) - 1);
+#pragma unroll
+      for (int j = 0; j < K; ++j) idx = insert_zero_bit(idx, op.tq[j]);
+      active = (idx & lc_mask) == lc_val;
+    }
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r].x = acc[r].y = 0;
+      const V* Mrow = M + ((h * R) << K);
+#pragma unroll(K <= 3 ? D : 2)
+      for (int c = 0; c < D; ++c) {
+        uint32_t off = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) off |= ((c >> j) & 1) ? bit[j] : 0u;
+        const V v = sm[idx | off];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const V m = __ldg(&Mrow[(r << K) | c]);
+          if (REAL) {
+            acc[r].x = fma(m.x, v.x, acc[r].x);
+            acc[r].y = fma(m.x, v.y, acc[r].y);
+          } else {
+            cfma(acc[r], m, v);
+          }
+        }
+      }
+    }
+    if (S > 1) __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = h * R + r;
+        uint32_t off = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) off |= ((row >> j) & 1) ? bit[j] : 0u;
+        sm[idx | off] = acc[r];
+      }
+    }
+    if (S > 1 && it0 + THREADS < nitems) __syncthreads();
+  }
+}
+
+// ---- DIAG: amp *= table[bits of the (global) index] -----------------------------------------------
+template <typename V, int THREADS>
+__device__ __forceinline__ void op_diag(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ table,
+                                        uint64_t gbase, int tid) {
+  const uint32_t xidx = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg);
+  const int nl = op.n_lseg;
+  QlsSeg ls[QLS_MAX_SEG];
+#pragma unroll
+  for (int i = 0; i < QLS_MAX_SEG; ++i) ls[i] = op.lseg[i];
+  const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+  const int n = 1 << T;
+  for (int i = tid; i < n; i += THREADS) {
+    if ((i & lc_mask) != lc_val) continue;
+    uint32_t ti = xidx;
+#pragma unroll
+    for (int s = 0; s < QLS_MAX_SEG; ++s)
+      if (s < nl) ti |= ((i >> ls[s].src) & ((1u << ls[s].width) - 1u)) << ls[s].dst;
+    sm[i] = cmul(sm[i], __ldg(&table[ti]));
+  }
+}
+
+// ---- MUXRY: RY(angle[index bits]) on one tile-local qubit; table entries are (cos, sin) of angle/2 -
+template <typename V, int THREADS>
+__device__ __forceinline__ void op_muxry(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ table,
+                                         uint64_t gbase, int tid) {
+  const uint32_t xidx = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg);
+  const int nl = op.n_lseg;
+  QlsSeg ls[QLS_MAX_SEG];
+#pragma unroll
+  for (int i = 0; i < QLS_MAX_SEG; ++i) ls[i] = op.lseg[i];
+  const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+  const uint32_t tq = op.tq[0];
+  const int n = 1 << (T - 1);
+  for (int g = tid; g < n; g += THREADS) {
+    const uint32_t i0 = insert_zero_bit(g, tq);
+    if ((i0 & lc_mask) != lc_val) continue;
+    uint32_t ti = xidx;
+#pragma unroll
+    for (int s = 0; s < QLS_MAX_SEG; ++s)
+      if (s < nl) ti |= ((i0 >> ls[s].src) & ((1u << ls[s].width) - 1u)) << ls[s].dst;
+    const V cs = __ldg(&table[ti]);
+    const uint32_t i1 = i0 | (1u << tq);
+    const V a0 = sm[i0], a1 = sm[i1];
+    V b0, b1;
+    b0.x = cs.x * a0.x - cs.y * a1.x;
+    b0.y = cs.x * a0.y - cs.y * a1.y;
+    b1.x = cs.y * a0.x + cs.x * a1.x;
+    b1.y = cs.y * a0.y + cs.x * a1.y;
+    sm[i0] = b0;
+    sm[i1] = b1;
+  }
+}
+
+// ---- dispatcher ------------------------------------------------------------------------------------
+// Applies ops[0..n_ops) to the tile; every thread of the block must call it.  gbase = global index
+// of tile-local index 0 (external controls and table fields outside the tile are read from it).
+template <typename V, int THREADS, bool HEAVY>
+__device__ __forceinline__ void apply_ops(V* __restrict__ sm, int T, const QlsOp* __restrict__ ops, int n_ops,
+                                          const unsigned char* __restrict__ pool, uint64_t gbase, int tid) {
+  for (int o = 0; o < n_ops; ++o) {
+    const QlsOp& op = ops[o];
+    if ((gbase & op.xc_mask) != op.xc_val) continue;  // block-uniform
+    const V* data = reinterpret_cast<const V*>(pool + op.pool_off);
+    const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
+    switch (op.kind) {
+      case QLS_OP_DENSE:
+        switch (op.k) {
+          case 1:
+            if (real) op_dense<V, 1, 1, THREADS, true>(sm, T, op, data, tid);
+            else op_dense<V, 1, 1, THREADS, false>(sm, T, op, data, tid);
+            break;
+          case 2:
+            if (real) op_dense<V, 2, 1, THREADS, true>(sm, T, op, data, tid);
+            else op_dense<V, 2, 1, THREADS, false>(sm, T, op, data, tid);
+            break;
+          case 3:
+            op_dense<V, 3, 1, THREADS, false>(sm, T, op, data, tid);
+            break;
+          case 4:
+            if (HEAVY) op_dense<V, 4, 1, THREADS, false>(sm, T, op, data, tid);
+            break;
+          case 5:
+            if (HEAVY) op_dense<V, 5, 2, THREADS, false>(sm, T, op, data, tid);
+            break;
+        }
+        break;
+      case QLS_OP_DIAG:
+        op_diag<V, THREADS>(sm, T, op, data, gbase, tid);
+        break;
+      case QLS_OP_MUXRY:
+        op_muxry<V, THREADS>(sm, T, op, data, gbase, tid);
+        break;
+    }
+    __syncthreads();
+  }
+}

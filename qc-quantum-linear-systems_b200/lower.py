@@ -1,0 +1,602 @@
+"""Circuit lowering: leaf gate stream -> fused blocks -> tile passes -> binary program.
+
+Replaces the per-gate loop of ``Statevector._evolve_instruction`` (reference call site
+``hhl_qiskit_implementation.py:49``) by:
+
+1. **normalise**  every leaf becomes a dense block (k <= 5 targets + symbolic controls), a
+   diagonal block (phase table over its qubits), a multiplexed-RY block (``UCRYGate`` and its
+   controlled forms -- the eigenvalue inversion), an initialisation, or a GEMM block (dense
+   ``e^{iAt}`` power on the low data register);
+2. **fuse**       diagonal runs are merged (the ``cp`` ladders of the QFT inside QPE), RY
+   multiplexers on the same target add their angle tables (``ExactReciprocal`` = one block), and
+   neighbouring small dense gates are multiplied into k <= ``max_fuse_qubits`` unitaries;
+3. **group**      consecutive blocks whose non-low target qubits fit the tile share one *pass*:
+   one HBM read + write of the state, all blocks applied in shared memory;
+4. **emit**       ``QlsPass`` / ``QlsOp`` records + constant pool (``include/qls_abi.h``).
+
+The input circuit is never mutated (QASM / depth / width come from the un-fused circuit).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+from .circuit import Leaf, QuantumCircuit, flatten
+
+# --------------------------------------------------------------------------------------
+# Blocks
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class Block:
+    kind: str  # "dense" | "diag" | "muxry" | "init" | "gemm"
+    targets: Tuple[int, ...] = ()  # dense: matrix-bit order; muxry: (target,); diag: table qubits
+    controls: Dict[int, int] = field(default_factory=dict)
+    matrix: Optional[np.ndarray] = None  # dense / gemm
+    factors: List[Tuple[Tuple[int, ...], np.ndarray]] = field(default_factory=list)  # diag
+    selectors: Tuple[int, ...] = ()  # muxry: table-bit order
+    angles: Optional[np.ndarray] = None  # muxry
+    amps: Optional[np.ndarray] = None  # init
+    n_source: int = 1  # leaf gates folded into this block
+
+    @property
+    def touched(self) -> frozenset:
+        """Qubits acted on non-diagonally."""
+        if self.kind in ("dense", "gemm", "init"):
+            return frozenset(self.targets)
+        if self.kind == "muxry":
+            return frozenset(self.targets[:1])
+        return frozenset()
+
+    @property
+    def support(self) -> frozenset:
+        s = set(self.targets) | set(self.controls) | set(self.selectors)
+        return frozenset(s)
+
+
+def _commutes(a: Block, b: Block) -> bool:
+    """Sufficient (not necessary) condition for two blocks to commute: neither acts
+    non-diagonally on a qubit the other one uses at all.  (Controls, selectors and diagonal
+    tables are all diagonal in the computational basis.)"""
+    if a.touched & b.support:
+        return False
+    if b.touched & a.support:
+        return False
+    return True
+
+
+def _is_diagonal(m: np.ndarray) -> bool:
+    return np.count_nonzero(m - np.diag(np.diagonal(m))) == 0
+
+
+def _fold_controls_diag(qubits: Tuple[int, ...], table: np.ndarray, controls: Dict[int, int]):
+    """A controlled diagonal is a diagonal over controls + targets."""
+    if not controls:
+        return qubits, table
+    cq = tuple(controls)
+    nq = len(qubits)
+    full = np.ones(2 ** (nq + len(cq)), dtype=complex)
+    idx = np.arange(full.size)
+    ok = np.ones(full.size, dtype=bool)
+    for j, q in enumerate(cq):
+        ok &= ((idx >> (nq + j)) & 1) == controls[q]
+    full[ok] = table[idx[ok] & (2**nq - 1)]
+    return qubits + cq, full
+
+
+def normalise(leaves: Sequence[Leaf], max_dense: int = 5) -> List[Block]:
+    out: List[Block] = []
+    for lf in leaves:
+        ctrl = {q: (lf.ctrl_state >> j) & 1 for j, q in enumerate(lf.controls)}
+        if lf.kind == "init":
+            out.append(Block("init", tuple(lf.targets), amps=np.asarray(lf.payload, dtype=complex)))
+        elif lf.kind == "diag":
+            qs, tab = _fold_controls_diag(tuple(lf.targets), np.asarray(lf.payload, dtype=complex), ctrl)
+            out.append(Block("diag", qs, factors=[(qs, tab)]))
+        elif lf.kind == "ucry":
+            tgt, sel = lf.targets[0], tuple(lf.targets[1:])
+            ang = np.asarray(lf.payload, dtype=float)
+            if ctrl:  # fold controls into the selector: angle 0 where the control is not satisfied
+                cq = tuple(ctrl)
+                ns = len(sel)
+                full = np.zeros(2 ** (ns + len(cq)))
+                idx = np.arange(full.size)
+                ok = np.ones(full.size, dtype=bool)
+                for j, q in enumerate(cq):
+                    ok &= ((idx >> (ns + j)) & 1) == ctrl[q]
+                full[ok] = ang[idx[ok] & (2**ns - 1)]
+                sel, ang = sel + cq, full
+            out.append(Block("muxry", (tgt,), selectors=sel, angles=ang))
+        elif lf.kind == "dense":
+            m = np.asarray(lf.payload, dtype=complex)
+            k = len(lf.targets)
+            if _is_diagonal(m) and k + len(ctrl) <= 10:
+                qs, tab = _fold_controls_diag(tuple(lf.targets), np.diagonal(m).copy(), ctrl)
+                out.append(Block("diag", qs, factors=[(qs, tab)]))
+            elif k <= max_dense:
+                out.append(Block("dense", tuple(lf.targets), ctrl, m))
+            else:
+                order = np.argsort(lf.targets)
+                if sorted(lf.targets) != list(range(k)):
+                    raise NotImplementedError(
+                        f"dense {k}-qubit block must act on the low qubits 0..{k-1} (GEMM block); got {lf.targets}"
+                    )
+                if list(order) != list(range(k)):
+                    m = _permute_matrix(m, [lf.targets.index(q) for q in range(k)])
+                out.append(Block("gemm", tuple(range(k)), ctrl, m))
+        else:
+            raise ValueError(lf.kind)
+    return out
+
+
+def _permute_matrix(m: np.ndarray, new_from_old: Sequence[int]) -> np.ndarray:
+    """Matrix of the same gate with matrix bit ``j`` now being old matrix bit ``new_from_old[j]``."""
+    k = len(new_from_old)
+    idx = np.arange(2**k)
+    old = np.zeros_like(idx)
+    for j, o in enumerate(new_from_old):
+        old |= ((idx >> j) & 1) << o
+    return m[np.ix_(old, old)]
+
+
+def _expand_dense(b: Block, qubits: Tuple[int, ...]) -> np.ndarray:
+    """Full matrix of a dense block (controls folded in) on the ordered qubit tuple ``qubits``."""
+    k = len(qubits)
+    pos = {q: j for j, q in enumerate(qubits)}
+    dim = 2**k
+    full = np.zeros((dim, dim), dtype=complex)
+    tpos = [pos[q] for q in b.targets]
+    tmask = sum(1 << p for p in tpos)
+    idx = np.arange(dim)
+    ok = np.ones(dim, dtype=bool)
+    for q, v in b.controls.items():
+        ok &= ((idx >> pos[q]) & 1) == v
+    sub = np.zeros(dim, dtype=np.int64)
+    for j, p in enumerate(tpos):
+        sub |= ((idx >> p) & 1) << j
+    rest = idx & ~tmask
+    kt = len(tpos)
+    for col in range(dim):
+        if not ok[col]:
+            full[col, col] = 1.0
+            continue
+        for r in range(2**kt):
+            row = rest[col]
+            for j, p in enumerate(tpos):
+                row |= ((r >> j) & 1) << p
+            full[row, col] = b.matrix[r, sub[col]]
+    return full
+
+
+def fuse(blocks: Sequence[Block], max_fuse_qubits: int = 3, max_diag_qubits: int = 10,
+         max_mux_selectors: int = 20) -> List[Block]:
+    out: List[Block] = []
+    for b in blocks:
+        if b.kind == "diag":
+            merged = False
+            for prev in reversed(out):
+                if prev.kind == "diag":
+                    union = set(prev.targets) | set(b.targets)
+                    if len(union) <= max_diag_qubits:
+                        prev.targets = tuple(sorted(union))
+                        prev.factors = prev.factors + b.factors
+                        prev.n_source += b.n_source
+                        merged = True
+                    break
+                if not _commutes(prev, b):
+                    break
+            if not merged:
+                out.append(Block("diag", tuple(sorted(b.targets)), factors=list(b.factors), n_source=b.n_source))
+            continue
+        if b.kind == "muxry":
+            merged = False
+            for prev in reversed(out):
+                if prev.kind == "muxry" and prev.targets == b.targets:
+                    union = list(prev.selectors) + [q for q in b.selectors if q not in prev.selectors]
+                    if len(union) <= max_mux_selectors:
+                        prev.angles = _mux_expand(prev.angles, prev.selectors, union) + _mux_expand(b.angles, b.selectors, union)
+                        prev.selectors = tuple(union)
+                        prev.n_source += b.n_source
+                        merged = True
+                    break
+                if not _commutes(prev, b):
+                    break
+            if not merged:
+                out.append(Block("muxry", b.targets, selectors=b.selectors, angles=np.array(b.angles), n_source=b.n_source))
+            continue
+        if b.kind == "dense":
+            cand = None
+            for prev in reversed(out):
+                if _commutes(prev, b):
+                    continue
+                cand = prev
+                break
+            if cand is not None and cand.kind == "dense":
+                union = tuple(sorted(cand.support | b.support))
+                small = len(b.support) <= 2 and len(cand.support) <= max_fuse_qubits
+                tunion = tuple(sorted(set(cand.targets) | set(b.targets)))
+                if cand.controls == b.controls and len(tunion) <= max(max_fuse_qubits, len(cand.targets), len(b.targets)):
+                    # same controls: multiply the target matrices, keep the controls symbolic
+                    ma = _expand_dense(Block("dense", cand.targets, {}, cand.matrix), tunion)
+                    mb = _expand_dense(Block("dense", b.targets, {}, b.matrix), tunion)
+                    cand.targets, cand.matrix = tunion, mb @ ma
+                    cand.n_source += b.n_source
+                    continue
+                if small and len(union) <= max_fuse_qubits:
+                    ma = _expand_dense(cand, union)
+                    mb = _expand_dense(b, union)
+                    cand.targets, cand.controls, cand.matrix = union, {}, mb @ ma
+                    cand.n_source += b.n_source
+                    continue
+            out.append(Block("dense", b.targets, dict(b.controls), b.matrix, n_source=b.n_source))
+            continue
+        out.append(b)
+    # a fused dense block may have become diagonal or the identity
+    final: List[Block] = []
+    for b in out:
+        if b.kind == "dense" and not b.controls and _is_diagonal(b.matrix):
+            d = np.diagonal(b.matrix).copy()
+            if np.allclose(d, 1.0, atol=0, rtol=0):
+                continue
+            final.append(Block("diag", b.targets, factors=[(b.targets, d)], n_source=b.n_source))
+        else:
+            final.append(b)
+    return final
+
+
+def _mux_expand(angles: np.ndarray, sel: Sequence[int], union: Sequence[int]) -> np.ndarray:
+    """Angle table over ``union`` (bit j = union[j]) of a table over ``sel``."""
+    idx = np.arange(2 ** len(union))
+    sub = np.zeros_like(idx)
+    upos = {q: j for j, q in enumerate(union)}
+    for j, q in enumerate(sel):
+        sub |= ((idx >> upos[q]) & 1) << j
+    return np.asarray(angles, dtype=float)[sub]
+
+
+# --------------------------------------------------------------------------------------
+# Pass grouping + emission
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class LoweringOptions:
+    dtype: str = "fp64"  # "fp64" (complex128) | "fp32" (complex64)
+    tile_bits: int = 0  # 0 -> 12 (fp64) / 13 (fp32)
+    max_high: int = 5  # tile qubits above the contiguous low run
+    max_fuse_qubits: int = 3
+    max_diag_qubits: int = 10
+    n_local: int = 0  # 0 -> all qubits local (single GPU)
+
+    def resolved_tile_bits(self) -> int:
+        return self.tile_bits or (12 if self.dtype == "fp64" else 13)
+
+
+@dataclass
+class Step:
+    kind: str  # "passes" | "init" | "gemm"
+    pass_begin: int = 0
+    pass_end: int = 0
+    qubits: Tuple[int, ...] = ()
+    amps: Optional[np.ndarray] = None
+    nb: int = 0
+    ctrl_mask: int = 0
+    ctrl_val: int = 0
+    matrix: Optional[np.ndarray] = None
+
+
+@dataclass
+class PassInfo:
+    """Host-side description of one emitted pass (accounting for the roofline)."""
+    tile_bits: int
+    low_bits: int
+    high: Tuple[int, ...]
+    fixed_bits: int
+    n_ops: int
+    n_source: int
+    op_controls: List[int]
+    heavy: bool
+
+
+@dataclass
+class LoweredProgram:
+    num_qubits: int
+    n_local: int
+    dtype: str
+    steps: List[Step]
+    passes: "C.Array"
+    ops: "C.Array"
+    pool: np.ndarray
+    pass_info: List[PassInfo]
+    n_source_gates: int
+    global_phase: float
+
+    @property
+    def n_passes(self) -> int:
+        return len(self.pass_info)
+
+    def amp_bytes(self) -> int:
+        return 16 if self.dtype == "fp64" else 8
+
+    def pass_bytes(self, i: int, n_local: Optional[int] = None) -> int:
+        """Algorithmic HBM bytes of pass ``i``: one read + one write of every touched amplitude
+        (``2*S*2**(n-c)``)."""
+        n = self.n_local if n_local is None else n_local
+        return 2 * self.amp_bytes() * 2 ** (n - self.pass_info[i].fixed_bits)
+
+    def total_pass_bytes(self) -> int:
+        return sum(self.pass_bytes(i) for i in range(self.n_passes))
+
+    def amp_updates(self) -> int:
+        """Sum over fused blocks of ``2**(n-c)``."""
+        tot = 0
+        for p in self.pass_info:
+            for c in p.op_controls:
+                tot += 2 ** (self.n_local - c)
+        for s in self.steps:
+            if s.kind == "gemm":
+                tot += 2 ** (self.n_local - bin(s.ctrl_mask & (2**self.n_local - 1)).count("1"))
+        return tot
+
+
+def _segments(pairs: List[Tuple[int, int]]) -> List[Tuple[int, int, int]]:
+    """(src, dst) single-bit moves -> merged (src, width, dst) fields."""
+    segs: List[List[int]] = []
+    for src, dst in pairs:
+        if segs and segs[-1][0] + segs[-1][1] == src and segs[-1][2] + segs[-1][1] == dst:
+            segs[-1][1] += 1
+        else:
+            segs.append([src, 1, dst])
+    return [tuple(s) for s in segs]
+
+
+class _Emitter:
+    def __init__(self, n: int, opts: LoweringOptions):
+        self.n = n
+        self.opts = opts
+        self.n_local = opts.n_local or n
+        self.T = min(opts.resolved_tile_bits(), self.n_local)
+        self.Hmax = min(opts.max_high, self.T)
+        self.Lmin = self.T - self.Hmax
+        if opts.dtype == "fp32" and self.Lmin < 1:
+            self.Lmin = min(1, self.T)
+            self.Hmax = self.T - self.Lmin
+        self.cdtype = np.complex128 if opts.dtype == "fp64" else np.complex64
+        self.passes: List[_abi.QlsPass] = []
+        self.ops: List[_abi.QlsOp] = []
+        self.pool = bytearray()
+        self.pass_info: List[PassInfo] = []
+        self.steps: List[Step] = []
+        self.cur: List[Block] = []
+        self.cur_high: set = set()
+
+    # -- pool -----------------------------------------------------------------------------
+    def _pool_add(self, arr: np.ndarray) -> int:
+        while len(self.pool) % 16:
+            self.pool.append(0)
+        off = len(self.pool)
+        self.pool += np.ascontiguousarray(arr, dtype=self.cdtype).tobytes()
+        return off
+
+    # -- grouping -------------------------------------------------------------------------
+    def _fit(self, needed: set, l_floor: int):
+        """Largest contiguous low run L >= l_floor such that the touched qubits >= L fit the
+        remaining T - L tile bits; returns (L, high qubits) or None."""
+        n_loc = self.n_local
+        for L in range(self.T, l_floor - 1, -1):
+            high = {q for q in needed if q >= L}
+            if len(high) <= self.T - L and self.T - L <= _abi.QLS_MAX_HIGH:
+                q = L
+                while len(high) < self.T - L:  # pad with the next unused qubits above the low run
+                    if q >= n_loc:
+                        break
+                    if q not in high:
+                        high.add(q)
+                    q += 1
+                if len(high) == self.T - L:
+                    return L, high
+        return None
+
+    def add(self, b: Block) -> None:
+        if b.kind in ("init", "gemm"):
+            self.flush()
+            if b.kind == "init":
+                self.steps.append(Step("init", qubits=b.targets, amps=b.amps))
+            else:
+                mask = sum(1 << q for q in b.controls)
+                val = sum(v << q for q, v in b.controls.items())
+                self.steps.append(Step("gemm", nb=len(b.targets), ctrl_mask=mask, ctrl_val=val, matrix=b.matrix))
+            return
+        if any(q >= self.n_local for q in b.touched):
+            raise ValueError(f"block acts on non-local qubit(s) {sorted(b.touched)}; remap first (shard planner)")
+        need = set(b.touched)
+        if self.cur and self._fit(self.cur_high | need, self.Lmin) is None:
+            self.flush()
+        floor = 1 if self.opts.dtype == "fp32" else 0
+        if self._fit(self.cur_high | need, min(floor, self.T)) is None:
+            raise ValueError(f"block touching {sorted(need)} does not fit a tile of {self.T} bits")
+        self.cur.append(b)
+        self.cur_high |= need
+
+    def flush(self) -> None:
+        if not self.cur:
+            return
+        blocks, self.cur = self.cur, []
+        needed = set(self.cur_high)
+        self.cur_high = set()
+        T = self.T
+        floor = 1 if self.opts.dtype == "fp32" else 0
+        fit = self._fit(needed, self.Lmin) or self._fit(needed, min(floor, T))
+        L, high = fit
+        high_sorted = tuple(sorted(high))
+        L = T - len(high_sorted)
+        local_pos = {q: q for q in range(L)}
+        for j, q in enumerate(high_sorted):
+            local_pos[q] = L + j
+
+        # pass-level controls: external control bits shared by every op (tile skipping)
+        common: Optional[Dict[int, int]] = None
+        for b in blocks:
+            ext = {q: v for q, v in b.controls.items() if q not in local_pos and q < self.n_local} if b.kind == "dense" else {}
+            common = ext if common is None else {q: v for q, v in common.items() if ext.get(q) == v}
+        common = common or {}
+        fix_mask = sum(1 << q for q in common)
+        fix_val = sum(v << q for q, v in common.items())
+
+        op_begin = len(self.ops)
+        op_controls: List[int] = []
+        heavy = False
+        n_source = 0
+        for b in blocks:
+            n_source += b.n_source
+            for op, nctrl in self._emit_block(b, local_pos, T):
+                self.ops.append(op)
+                op_controls.append(nctrl)
+                heavy |= op.kind == _abi.QLS_OP_DENSE and op.k >= 4
+
+        p = _abi.QlsPass()
+        p.tile_bits, p.low_bits, p.n_high = T, L, len(high_sorted)
+        for j, q in enumerate(high_sorted):
+            p.high[j] = q
+        p.op_begin, p.op_count = op_begin, len(self.ops) - op_begin
+        p.fix_mask, p.fix_val = fix_mask, fix_val
+        free = [q for q in range(self.n_local) if q not in local_pos and not (fix_mask >> q) & 1]
+        segs = _segments([(j, q) for j, q in enumerate(free)])
+        if len(segs) > _abi.QLS_MAX_FSEG:
+            raise ValueError("tile counter deposit needs too many segments")
+        p.n_fseg = len(segs)
+        for j, (src, w, dst) in enumerate(segs):
+            p.fseg[j].src, p.fseg[j].width, p.fseg[j].dst = src, w, dst
+        idx = len(self.passes)
+        self.passes.append(p)
+        self.pass_info.append(PassInfo(T, L, high_sorted, len(common), p.op_count, n_source, op_controls, heavy))
+        if self.steps and self.steps[-1].kind == "passes" and self.steps[-1].pass_end == idx:
+            self.steps[-1].pass_end = idx + 1
+        else:
+            self.steps.append(Step("passes", pass_begin=idx, pass_end=idx + 1))
+
+    # -- op emission ----------------------------------------------------------------------
+    def _controls(self, op: _abi.QlsOp, controls: Dict[int, int], local_pos: Dict[int, int]) -> None:
+        for q, v in controls.items():
+            if q in local_pos:
+                op.lc_mask |= 1 << local_pos[q]
+                op.lc_val |= v << local_pos[q]
+            else:
+                op.xc_mask |= 1 << q
+                op.xc_val |= v << q
+
+    def _table_fields(self, op: _abi.QlsOp, qubits: Sequence[int], local_pos: Dict[int, int]) -> bool:
+        """Index fields for a table whose bit j is ``qubits[j]`` (ascending).  False if too many."""
+        lpairs = [(local_pos[q], j) for j, q in enumerate(qubits) if q in local_pos]
+        xpairs = [(q, j) for j, q in enumerate(qubits) if q not in local_pos]
+        lpairs.sort()
+        ls, xs = _segments(lpairs), _segments(xpairs)
+        if len(ls) > _abi.QLS_MAX_SEG or len(xs) > _abi.QLS_MAX_SEG:
+            return False
+        op.n_lseg, op.n_xseg = len(ls), len(xs)
+        for j, (src, w, dst) in enumerate(ls):
+            op.lseg[j].src, op.lseg[j].width, op.lseg[j].dst = src, w, dst
+        for j, (src, w, dst) in enumerate(xs):
+            op.xseg[j].src, op.xseg[j].width, op.xseg[j].dst = src, w, dst
+        return True
+
+    def _emit_block(self, b: Block, local_pos: Dict[int, int], T: int):
+        if b.kind == "dense":
+            op = _abi.QlsOp()
+            op.kind, op.k = _abi.QLS_OP_DENSE, len(b.targets)
+            lp = [local_pos[q] for q in b.targets]
+            order = sorted(range(len(lp)), key=lambda j: lp[j])
+            m = b.matrix if order == list(range(len(lp))) else _permute_matrix(b.matrix, order)
+            for j, o in enumerate(order):
+                op.tq[j] = lp[o]
+            if not np.any(m.imag):
+                op.flags |= _abi.QLS_OP_FLAG_REAL
+            op.pool_off = self._pool_add(m)
+            self._controls(op, b.controls, local_pos)
+            yield op, len(b.controls)
+        elif b.kind == "muxry":
+            op = _abi.QlsOp()
+            op.kind, op.k = _abi.QLS_OP_MUXRY, 1
+            op.tq[0] = local_pos[b.targets[0]]
+            sel = sorted(b.selectors)
+            ang = _mux_expand(b.angles, b.selectors, sel) if list(sel) != list(b.selectors) else b.angles
+            if not self._table_fields(op, sel, local_pos):
+                raise NotImplementedError("multiplexed RY with too many scattered selector qubits")
+            tab = np.cos(ang / 2) + 1j * np.sin(ang / 2)  # (cos, sin) pairs
+            op.pool_off = self._pool_add(tab)
+            yield op, 0
+        elif b.kind == "diag":
+            # greedily regroup the factors so that every emitted table fits the field limit
+            groups: List[List[Tuple[Tuple[int, ...], np.ndarray]]] = []
+            cur: List[Tuple[Tuple[int, ...], np.ndarray]] = []
+            for f in b.factors:
+                trial = cur + [f]
+                qs = sorted({q for fq, _ in trial for q in fq})
+                probe = _abi.QlsOp()
+                if len(qs) <= self.opts.max_diag_qubits and self._table_fields(probe, qs, local_pos):
+                    cur = trial
+                else:
+                    if not cur:
+                        raise NotImplementedError(f"diagonal gate on too many scattered qubits: {f[0]}")
+                    groups.append(cur)
+                    cur = [f]
+            if cur:
+                groups.append(cur)
+            for g in groups:
+                qs = sorted({q for fq, _ in g for q in fq})
+                tab = np.ones(2 ** len(qs), dtype=complex)
+                pos = {q: j for j, q in enumerate(qs)}
+                idx = np.arange(tab.size)
+                for fq, ft in g:
+                    sub = np.zeros_like(idx)
+                    for j, q in enumerate(fq):
+                        sub |= ((idx >> pos[q]) & 1) << j
+                    tab *= ft[sub]
+                op = _abi.QlsOp()
+                op.kind = _abi.QLS_OP_DIAG
+                self._table_fields(op, qs, local_pos)
+                op.pool_off = self._pool_add(tab)
+                yield op, 0
+        else:
+            raise ValueError(b.kind)
+
+
+def lower_blocks(num_qubits: int, blocks: Sequence[Block], opts: LoweringOptions, global_phase: float = 0.0,
+                 n_source_gates: int = 0) -> LoweredProgram:
+    em = _Emitter(num_qubits, opts)
+    blocks = list(blocks)
+    if global_phase:
+        ph = np.array([np.exp(1j * global_phase)])
+        if blocks and blocks[0].kind == "init":
+            b0 = blocks[0]
+            blocks[0] = Block("init", b0.targets, amps=b0.amps * ph[0])
+        else:
+            blocks.insert(0, Block("diag", (), factors=[((), ph)], n_source=0))
+    for b in blocks:
+        em.add(b)
+    em.flush()
+    passes = (_abi.QlsPass * max(1, len(em.passes)))(*em.passes)
+    ops = (_abi.QlsOp * max(1, len(em.ops)))(*em.ops)
+    pool = np.frombuffer(bytes(em.pool) if em.pool else b"\0" * 16, dtype=np.uint8).copy()
+    return LoweredProgram(num_qubits, em.n_local, opts.dtype, em.steps, passes, ops, pool, em.pass_info,
+                          n_source_gates, global_phase)
+
+
+def lower_leaves(num_qubits: int, leaves: Sequence[Leaf], global_phase: float = 0.0,
+                 opts: Optional[LoweringOptions] = None, fused: bool = True) -> LoweredProgram:
+    opts = opts or LoweringOptions()
+    blocks = normalise(leaves)
+    if fused:
+        blocks = fuse(blocks, opts.max_fuse_qubits, opts.max_diag_qubits)
+    return lower_blocks(num_qubits, blocks, opts, global_phase, n_source_gates=len(leaves))
+
+
+def lower_circuit(circuit: QuantumCircuit, opts: Optional[LoweringOptions] = None, fused: bool = True) -> LoweredProgram:
+    leaves, phase = flatten(circuit)
+    return lower_leaves(circuit.num_qubits, leaves, phase, opts, fused)

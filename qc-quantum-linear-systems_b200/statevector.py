@@ -1,0 +1,94 @@
+"""``Statevector`` look-alike: the class the reference constructs at
+``hhl_qiskit_implementation.py:49`` and ``vqls_qiskit_implementation.py:65``
+(``qiskit.quantum_info.Statevector(circuit).data``).
+
+Construction from a circuit lowers it and evolves |0...0> on the GPU; ``.data`` copies the
+amplitudes back as a host ``complex128`` array (only sensible up to ~30 qubits -- use
+``read_slice`` / the reductions for larger states so the state never leaves HBM).
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy as np
+
+from .circuit import QuantumCircuit
+from .engine import DeviceProgram, DeviceState
+from .lower import LoweringOptions, lower_circuit
+
+_MAX_HOST_QUBITS = 31
+
+
+class Statevector:
+    def __init__(self, data: Any, precision: str = "fp64", device: Optional[int] = None,
+                 options: Optional[LoweringOptions] = None, fused: bool = True):
+        self.precision = precision
+        if isinstance(data, Statevector):
+            self._state, self.num_qubits, self.program = data._state, data.num_qubits, data.program
+            return
+        if isinstance(data, QuantumCircuit):
+            cached = getattr(data, "_sv_cache", None)
+            if cached is not None and cached.precision == precision and options is None and fused:
+                self._state, self.num_qubits, self.program = cached._state, cached.num_qubits, cached.program
+                return
+            opts = options or LoweringOptions(dtype=precision)
+            opts.dtype = precision
+            lowered = lower_circuit(data, opts, fused=fused)
+            self.num_qubits = data.num_qubits
+            self.program = DeviceProgram(lowered, device)
+            self._state = DeviceState(self.num_qubits, precision, device)
+            self.program.run(self._state)
+            return
+        arr = np.asarray(data).reshape(-1)
+        n = int(round(np.log2(arr.size)))
+        if 2**n != arr.size:
+            raise ValueError("statevector length must be a power of two")
+        self.num_qubits = n
+        self.program = None
+        self._state = DeviceState(n, precision, device)
+        self._state.write(0, arr)
+
+    # -- qiskit-shaped accessors ----------------------------------------------------------
+    @property
+    def dim(self) -> int:
+        return 2**self.num_qubits
+
+    @property
+    def data(self) -> np.ndarray:
+        if self.num_qubits > _MAX_HOST_QUBITS:
+            raise MemoryError(f"refusing to copy a {self.num_qubits}-qubit state to the host; use read_slice()")
+        return self._state.read().astype(np.complex128, copy=False)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.data if dtype is None else self.data.astype(dtype)
+
+    def __len__(self) -> int:
+        return self.dim
+
+    def read_slice(self, offset: int, count: int) -> np.ndarray:
+        return self._state.read(offset, count).astype(np.complex128, copy=False)
+
+    def expectation_value(self, oper: Any, qargs: Any = None) -> float:
+        """Only Z on one qubit is needed by the reference's path (Hadamard test).
+        ``oper`` may be ``("Z", q)`` or a Pauli label string like ``"IIZ"`` (rightmost = qubit 0)."""
+        if isinstance(oper, tuple) and oper[0].upper() == "Z":
+            return self._state.expectation_z(int(oper[1]))
+        if isinstance(oper, str):
+            label = oper.upper()
+            if set(label) <= {"I", "Z"} and label.count("Z") == 1 and len(label) == self.num_qubits:
+                return self._state.expectation_z(len(label) - 1 - label.index("Z"))
+        raise NotImplementedError("only single-qubit Z observables are supported")
+
+    # -- on-device reductions -------------------------------------------------------------
+    def norm_sq_range(self, offset: int, count: int) -> float:
+        return self._state.norm_sq_range(offset, count)
+
+    def probability(self, mask: int, value: int) -> float:
+        return self._state.prob_mask(mask, value)
+
+    def expectation_z(self, qubit: int) -> float:
+        return self._state.expectation_z(qubit)
+
+    def inner(self, other: "Statevector") -> complex:
+        """<other|self>"""
+        return self._state.inner(other._state)

@@ -1,0 +1,128 @@
+"""NumPy interpreter of the binary program format of ``include/qls_abi.h`` (test infrastructure).
+
+Executes ``QlsPass`` / ``QlsOp`` records with the semantics the CUDA kernels implement
+(``csrc/tile_pass.cu``, ``csrc/tile_ops.cuh``, ``csrc/ctrl_gemm.cu``), so that the lowering pass
+can be validated against the oracle in the GPU-less container.  It is NOT a product code path:
+nothing in the package imports it.
+"""
+import numpy as np
+
+from qls_b200 import _abi
+
+
+def _gather(x, segs, n):
+    r = np.zeros_like(x)
+    for i in range(n):
+        s = segs[i]
+        r |= ((x >> s.src) & ((1 << s.width) - 1)) << s.dst
+    return r
+
+
+def _insert_zero(x, pos):
+    low = x & ((1 << pos) - 1)
+    return ((x >> pos) << (pos + 1)) | low
+
+
+def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0):
+    T, L = p.tile_bits, p.low_bits
+    fixed = bin(p.fix_mask).count("1")
+    free_bits = n_local - T - fixed
+    tiles = np.arange(2**free_bits, dtype=np.int64)
+    base = _gather(tiles, p.fseg, p.n_fseg) | p.fix_val
+    i = np.arange(2**T, dtype=np.int64)
+    spread = i & ((1 << L) - 1)
+    r = i >> L
+    for j in range(p.n_high):
+        spread |= ((r >> j) & 1) << p.high[j]
+    G = base[:, None] | spread[None, :]
+    sm = state[G]  # tiles x 2^T
+    gbase = base | index_offset
+    esz = np.dtype(cdtype).itemsize
+    for o in range(p.op_begin, p.op_begin + p.op_count):
+        op = ops[o]
+        act = (gbase & op.xc_mask) == op.xc_val
+        if not act.any():
+            continue
+        if op.kind == _abi.QLS_OP_DENSE:
+            K = op.k
+            M = np.frombuffer(pool, dtype=cdtype, count=4**K, offset=op.pool_off).reshape(2**K, 2**K)
+            g = np.arange(2 ** (T - K), dtype=np.int64)
+            idx = g.copy()
+            for j in range(K):
+                idx = _insert_zero(idx, op.tq[j])
+            ok = (idx & op.lc_mask) == op.lc_val
+            idx = idx[ok]
+            offs = np.zeros(2**K, dtype=np.int64)
+            for c in range(2**K):
+                for j in range(K):
+                    if (c >> j) & 1:
+                        offs[c] |= 1 << op.tq[j]
+            cols = idx[:, None] | offs[None, :]  # groups x 2^K
+            sub = sm[np.ix_(act.nonzero()[0], cols.reshape(-1))].reshape(-1, len(idx), 2**K)
+            res = np.einsum("rc,tgc->tgr", M, sub)
+            sm[np.ix_(act.nonzero()[0], cols.reshape(-1))] = res.reshape(res.shape[0], -1)
+        elif op.kind == _abi.QLS_OP_DIAG:
+            n_tab = 1
+            for s in list(op.lseg)[: op.n_lseg] + list(op.xseg)[: op.n_xseg]:
+                n_tab = max(n_tab, 1 << (s.dst + s.width))
+            table = np.frombuffer(pool, dtype=cdtype, count=n_tab, offset=op.pool_off)
+            ti = _gather(gbase, op.xseg, op.n_xseg)[:, None] | _gather(i, op.lseg, op.n_lseg)[None, :]
+            ok = ((i & op.lc_mask) == op.lc_val)[None, :] & act[:, None]
+            fac = np.where(ok, table[ti], 1.0)
+            sm = (sm * fac).astype(cdtype)
+        elif op.kind == _abi.QLS_OP_MUXRY:
+            n_tab = 1
+            for s in list(op.lseg)[: op.n_lseg] + list(op.xseg)[: op.n_xseg]:
+                n_tab = max(n_tab, 1 << (s.dst + s.width))
+            table = np.frombuffer(pool, dtype=cdtype, count=n_tab, offset=op.pool_off)
+            tq = op.tq[0]
+            g = np.arange(2 ** (T - 1), dtype=np.int64)
+            i0 = _insert_zero(g, tq)
+            ok = (i0 & op.lc_mask) == op.lc_val
+            i0 = i0[ok]
+            i1 = i0 | (1 << tq)
+            ti = _gather(gbase, op.xseg, op.n_xseg)[:, None] | _gather(i0, op.lseg, op.n_lseg)[None, :]
+            cs = table[ti]
+            c, s_ = cs.real, cs.imag
+            a0, a1 = sm[:, i0], sm[:, i1]
+            b0 = c * a0 - s_ * a1
+            b1 = s_ * a0 + c * a1
+            m = act[:, None]
+            sm[:, i0] = np.where(m, b0, a0)
+            sm[:, i1] = np.where(m, b1, a1)
+        else:
+            raise ValueError(op.kind)
+    state[G] = sm
+    _ = esz
+
+
+def run_program(lowered, psi0=None, index_offset=0):
+    """Evolve |0...0> (or ``psi0``) through a LoweredProgram; returns the final local state."""
+    n = lowered.n_local
+    cdtype = np.complex128 if lowered.dtype == "fp64" else np.complex64
+    pool = lowered.pool.tobytes()
+    state = np.zeros(2**n, dtype=cdtype)
+    steps = list(lowered.steps)
+    if psi0 is not None:
+        state[:] = psi0
+    elif steps and steps[0].kind == "init":
+        s = steps.pop(0)
+        assert tuple(s.qubits) == tuple(range(len(s.qubits)))
+        if index_offset == 0:
+            state[: len(s.amps)] = s.amps
+    elif index_offset == 0:
+        state[0] = 1
+    for s in steps:
+        if s.kind == "passes":
+            for pi in range(s.pass_begin, s.pass_end):
+                run_pass(state, lowered.passes[pi], lowered.ops, pool, cdtype, n, index_offset)
+        elif s.kind == "gemm":
+            nb = s.nb
+            rows = np.arange(2 ** (n - nb), dtype=np.int64)
+            gidx = (rows << nb) | index_offset
+            sel = (gidx & s.ctrl_mask) == s.ctrl_val
+            mat = state.reshape(-1, 2**nb)
+            mat[sel] = (mat[sel] @ s.matrix.T).astype(cdtype)
+        else:
+            raise ValueError(s.kind)
+    return state

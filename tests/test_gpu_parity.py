@@ -1,0 +1,225 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Run on the B200 box:
+``python -m pytest tests -m gpu``.
+
+Tolerances (BASELINE.json north_star): per-amplitude |delta| <= 1e-12 in fp64 (1e-5 in fp32) and
+state fidelity >= 1 - 1e-10."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hhl_analytic, numpy_sv
+
+from _util import circuit_to_stream, random_circuit, random_unitary
+
+pytestmark = pytest.mark.gpu
+
+TOL64, TOL32, FID = 1e-12, 1e-5, 1 - 1e-10
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _fidelity(a, b):
+    return abs(np.vdot(a, b)) ** 2 / (np.vdot(a, a).real * np.vdot(b, b).real)
+
+
+def _gpu_state(qc, precision="fp64", **opt):
+    from qls_b200.lower import LoweringOptions
+    from qls_b200.statevector import Statevector
+
+    options = LoweringOptions(dtype=precision, **opt) if opt else None
+    return Statevector(qc, precision=precision, options=options)
+
+
+def test_library_loads_and_reports_b200(cuda_device):
+    import ctypes as C
+
+    from qls_b200 import _abi
+
+    lib = _abi.load()
+    sm, smem, tot, fr = C.c_int(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _abi.check(lib.qls_device_info(0, C.byref(sm), C.byref(smem), C.byref(tot), C.byref(fr)))
+    assert sm.value > 0 and smem.value >= 64 * 1024
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_circuits_fp64(cuda_device, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(3, 15))
+    qc = random_circuit(n, 60, rng, max_k=5)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = _gpu_state(qc).data
+    assert np.max(np.abs(got - want)) <= TOL64
+    assert _fidelity(got, want) >= FID
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("tile,high,fuse", [(5, 2, 1), (8, 3, 3), (12, 5, 4), (12, 5, 5), (10, 6, 2)])
+def test_random_circuits_tile_shapes(cuda_device, seed, tile, high, fuse):
+    rng = np.random.default_rng(2000 + seed)
+    n = int(rng.integers(6, 15))
+    qc = random_circuit(n, 50, rng, max_k=min(5, high + 1))
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = _gpu_state(qc, tile_bits=tile, max_high=high, max_fuse_qubits=fuse).data
+    assert np.max(np.abs(got - want)) <= TOL64
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_circuits_fp32(cuda_device, seed):
+    rng = np.random.default_rng(3000 + seed)
+    n = int(rng.integers(3, 15))
+    qc = random_circuit(n, 40, rng, max_k=4)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = _gpu_state(qc, precision="fp32").data
+    assert np.max(np.abs(got - want)) <= TOL32
+    assert _fidelity(got, want) >= 1 - 1e-5
+
+
+def test_random10_golden(cuda_device):
+    from qls_b200.statevector import Statevector
+
+    qc = random_circuit(10, 80, np.random.default_rng(424242), max_k=4)
+    want = np.load(os.path.join(GOLDEN, "random10_state.npy"))
+    assert np.max(np.abs(Statevector(qc).data - want)) <= TOL64
+
+
+def test_fused_equals_unfused(cuda_device):
+    from qls_b200.statevector import Statevector
+
+    rng = np.random.default_rng(5)
+    qc = random_circuit(13, 120, rng, max_k=3)
+    a = Statevector(qc, fused=True).data
+    b = Statevector(qc, fused=False).data
+    assert np.max(np.abs(a - b)) <= 1e-13
+
+
+def test_kat_hhl_2x2_through_the_facade(cuda_device, tmp_path, monkeypatch):
+    """Reference tests/test_hhl_implementations.py:23-29: width 5, x = [1.125, 0.375]."""
+    from qls_b200.quantum_linear_solver import QuantumLinearSolver
+    from qls_b200.toymodels import Qiskit4QubitExample
+
+    monkeypatch.chdir(tmp_path)
+    model = Qiskit4QubitExample()
+    qls = QuantumLinearSolver()
+    x = qls.solve(model.matrix_a, model.vector_b, method="hhl_qiskit", file_basename="kat")
+    assert qls.circuit_width == 5
+    assert np.allclose(model.classical_solution, x)
+    assert np.max(np.abs(x - np.array([1.125, 0.375]))) < 1e-12
+    assert os.path.exists("hhl_qiskit_circuit.qasm3")  # reference side effect, utils.py:12-13
+    assert qls.qasm_circuit.startswith("OPENQASM 3")
+    assert qls.run_time > 0 and qls.circuit_depth > 0
+
+
+def test_kat_state_matches_appendix_b(cuda_device):
+    from qls_b200.hhl import HHL
+    from qls_b200.statevector import Statevector
+    from qls_b200.toymodels import Qiskit4QubitExample
+
+    model = Qiskit4QubitExample()
+    qc = HHL(power_mode="repeat").construct_circuit(model.matrix_a, model.vector_b)
+    got = Statevector(qc).data
+    want = np.load(os.path.join(GOLDEN, "hhl_2x2_state.npy"))
+    assert np.max(np.abs(got - want)) <= TOL64
+
+
+@pytest.mark.parametrize("name", ["classiq_demo", "volterra2"])
+def test_hhl_toy_models_vs_golden(cuda_device, name):
+    from qls_b200.hhl import HHL
+    from qls_b200.statevector import Statevector
+    from qls_b200.toymodels import ClassiqDemoExample, VolterraProblem
+
+    model = ClassiqDemoExample() if name == "classiq_demo" else VolterraProblem(2)
+    hhl = HHL()
+    res = hhl.solve(model.matrix_a, model.vector_b)
+    got = Statevector(res.state).data
+    want = np.load(os.path.join(GOLDEN, f"hhl_{name}_state.npy"))
+    assert np.max(np.abs(got - want)) <= TOL64
+    assert _fidelity(got, want) >= FID
+    n = model.matrix_a.shape[0]
+    assert math.isclose(res.euclidean_norm, numpy_sv.hhl_norm(want, n, hhl.scaling), rel_tol=1e-12)
+
+
+def test_hhl_gemm_block_path(cuda_device):
+    """Dense controlled-e^{iAt} blocks on a 6-qubit data register go through qls_ctrl_gemm."""
+    from qls_b200.hhl import HHL
+    from qls_b200.lower import lower_circuit
+    from qls_b200.statevector import Statevector
+    from qls_b200.toymodels import TridiagonalToeplitz
+
+    model = TridiagonalToeplitz(6)
+    hhl = HHL(power_mode="eig")
+    qc = hhl.construct_circuit(model.matrix_a, model.vector_b)
+    assert any(s.kind == "gemm" for s in lower_circuit(qc).steps)
+    got = Statevector(qc).data
+    want = hhl_analytic.hhl_state(model.matrix_a, model.vector_b)
+    assert np.max(np.abs(got - want)) <= 5e-12  # 2*nl dense 64x64 products: a few more roundings
+    assert _fidelity(got, want) >= FID
+
+
+def test_reductions(cuda_device):
+    from qls_b200.statevector import Statevector
+
+    rng = np.random.default_rng(77)
+    n = 15
+    psi = rng.standard_normal(2**n) + 1j * rng.standard_normal(2**n)
+    psi /= np.linalg.norm(psi)
+    phi = rng.standard_normal(2**n) + 1j * rng.standard_normal(2**n)
+    phi /= np.linalg.norm(phi)
+    sv, sw = Statevector(psi), Statevector(phi)
+    assert np.array_equal(sv.data, psi)  # write/read round trip is bit exact
+    assert abs(sv.norm_sq_range(0, 2**n) - 1.0) < 1e-13
+    assert abs(sv.norm_sq_range(2 ** (n - 1), 64) - np.sum(np.abs(psi[2 ** (n - 1):2 ** (n - 1) + 64]) ** 2)) < 1e-15
+    assert sv.norm_sq_range(5, 0) == 0.0
+    for q in (0, 7, n - 1):
+        assert abs(sv.expectation_z(q) - numpy_sv.expectation_z(psi, q)) < 1e-13
+    assert abs(sv.expectation_value("I" * (n - 1) + "Z") - numpy_sv.expectation_z(psi, 0)) < 1e-13
+    mask, val = (1 << (n - 1)) | 0b110, (1 << (n - 1)) | 0b010
+    assert abs(sv.probability(mask, val) - numpy_sv.prob_mask(psi, mask, val)) < 1e-13
+    assert abs(sv.inner(sw) - np.vdot(phi, psi)) < 1e-13
+
+
+def test_hhl_shaped_vs_oracle(cuda_device):
+    from qls_b200.statevector import Statevector
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    n = 17
+    qc = hhl_shaped_circuit(n)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = Statevector(qc).data
+    assert np.max(np.abs(got - want)) <= TOL64
+    assert _fidelity(got, want) >= FID
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-11), ("fp32", 2e-4)])
+def test_large_state_properties(cuda_device, precision, tol):
+    """Size-independent checks at a size the oracle cannot reach: unit norm, P(flag) consistency,
+    and U^dagger U = identity (evolve, then evolve the inverse circuit, compare with the input)."""
+    from qls_b200.engine import DeviceProgram, DeviceState
+    from qls_b200.lower import LoweringOptions, lower_circuit
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    n = 27
+    qc = hhl_shaped_circuit(n)
+    opts = LoweringOptions(dtype=precision)
+    fwd = DeviceProgram(lower_circuit(qc, opts))
+    # inverse of everything after the state preparation (whose inverse is not an initialisation)
+    from qls_b200.circuit import Instruction, QuantumCircuit
+    inv_circ = QuantumCircuit(*qc.qregs, name="inv")
+    for ins in reversed(qc.data[1:]):
+        inv_circ.data.append(Instruction(ins.operation.inverse(), ins.qubits))
+    bwd = DeviceProgram(lower_circuit(inv_circ, LoweringOptions(dtype=precision)))
+    st = DeviceState(n, precision)
+    fwd.run(st)
+    assert abs(st.norm_sq_range(0, 2**n) - 1.0) < tol
+    p1 = st.prob_mask(1 << (n - 1), 1 << (n - 1))
+    p0 = st.prob_mask(1 << (n - 1), 0)
+    assert abs(p0 + p1 - 1.0) < tol and 0.0 < p1 < 1.0
+    assert abs(st.expectation_z(n - 1) - (p0 - p1)) < tol
+    bwd.run(st, initialise=False)
+    nb = qc.qregs[0].size
+    rng = np.random.default_rng(99)
+    b = rng.standard_normal(2**nb)
+    b /= np.linalg.norm(b)
+    back = st.read(0, 2**nb)
+    assert np.max(np.abs(back - b)) < tol * 10
+    assert abs(st.norm_sq_range(0, 2**nb) - 1.0) < tol * 10

@@ -1,0 +1,127 @@
+"""Lowering pass vs the oracle, through the NumPy interpreter of the binary program format
+(``tests/_emulator.py``): fusion, pass grouping, control handling and table fields are all
+validated on the CPU; the GPU tests then only have to prove the kernels match the same format."""
+import numpy as np
+import pytest
+
+from oracle import numpy_sv
+from qls_b200.circuit import QuantumCircuit, flatten
+from qls_b200.hhl import HHL
+from qls_b200.library import QFT
+from qls_b200.lower import LoweringOptions, lower_circuit
+from qls_b200.toymodels import ClassiqDemoExample, Qiskit4QubitExample, VolterraProblem
+
+from _emulator import run_program
+from _util import circuit_to_stream, random_circuit
+
+
+def _check(qc, opts, fused=True, tol=1e-12):
+    want = numpy_sv.run(qc.num_qubits, circuit_to_stream(qc))
+    low = lower_circuit(qc, opts, fused=fused)
+    got = run_program(low)
+    assert np.max(np.abs(got - want)) < tol
+    return low
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("fused", [False, True])
+def test_random_circuits(seed, fused):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(3, 11))
+    qc = random_circuit(n, 40, rng, max_k=4)
+    opts = LoweringOptions(tile_bits=int(rng.integers(3, 8)), max_high=int(rng.integers(1, 4)),
+                           max_fuse_qubits=int(rng.integers(1, 5)))
+    _check(qc, opts, fused)
+
+
+def test_fusion_invariance_and_fewer_passes():
+    rng = np.random.default_rng(7)
+    qc = random_circuit(9, 80, rng, max_k=2)
+    opts = LoweringOptions(tile_bits=6, max_high=3)
+    a = _check(qc, opts, fused=False)
+    b = _check(qc, opts, fused=True)
+    assert sum(p.n_ops for p in b.pass_info) < sum(p.n_ops for p in a.pass_info)
+    assert np.max(np.abs(run_program(a) - run_program(b))) < 1e-13
+
+
+def test_does_not_mutate_circuit():
+    rng = np.random.default_rng(3)
+    qc = random_circuit(5, 20, rng)
+    before = [(i.operation.name, i.qubits) for i in qc.data]
+    lower_circuit(qc, LoweringOptions(tile_bits=4, max_high=2))
+    assert before == [(i.operation.name, i.qubits) for i in qc.data]
+
+
+@pytest.mark.parametrize("m", [3, 6, 9])
+def test_qft_is_few_diag_runs(m):
+    qc = QuantumCircuit(m)
+    qc.h(0)
+    qc.compose(QFT(m, inverse=True, do_swaps=False).reverse_bits(), inplace=True)
+    low = _check(qc, LoweringOptions(tile_bits=5, max_high=2))
+    # m H gates, m(m-1)/2 controlled phases -> at most ~2m ops after merging the ladders
+    assert sum(p.n_ops for p in low.pass_info) <= 2 * m + 2
+
+
+@pytest.mark.parametrize("model_cls", [Qiskit4QubitExample, ClassiqDemoExample, lambda: VolterraProblem(2)])
+@pytest.mark.parametrize("mode", ["repeat", "eig"])
+def test_hhl_circuits(model_cls, mode):
+    model = model_cls()
+    if mode == "repeat" and model.matrix_a.shape[0] > 4:
+        pytest.skip("slow in the CPU oracle")
+    qc = HHL(power_mode=mode).construct_circuit(model.matrix_a, model.vector_b)
+    low = _check(qc, LoweringOptions(tile_bits=6, max_high=3))
+    # ExactReciprocal (UCRY + 2 controlled UCRY) must collapse to a single multiplexed-RY block
+    from qls_b200 import _abi
+    kinds = [low.ops[i].kind for i in range(sum(p.n_ops for p in low.pass_info))]
+    assert kinds.count(_abi.QLS_OP_MUXRY) == 1
+
+
+def test_fp32_program():
+    rng = np.random.default_rng(11)
+    qc = random_circuit(8, 40, rng)
+    want = numpy_sv.run(8, circuit_to_stream(qc))
+    low = lower_circuit(qc, LoweringOptions(dtype="fp32", tile_bits=6, max_high=3))
+    got = run_program(low)
+    assert got.dtype == np.complex64
+    assert np.max(np.abs(got - want)) < 1e-5
+
+
+def test_pass_level_control_skips_tiles():
+    # controlled blocks whose (shared) control is outside the tile touch only half the tiles
+    rng = np.random.default_rng(5)
+    from _util import random_unitary
+    from qls_b200.circuit import Gate
+    n = 10
+    qc = QuantumCircuit(n)
+    qc.append(Gate("unitary", 2, [], random_unitary(2, rng)).control(1), [9, 0, 1])
+    qc.append(Gate("unitary", 1, [], random_unitary(1, rng)).control(1), [9, 3])
+    psi0 = rng.standard_normal(2**n) + 1j * rng.standard_normal(2**n)
+    psi0 /= np.linalg.norm(psi0)
+    want = numpy_sv.run(n, circuit_to_stream(qc), psi0=psi0)
+    low = lower_circuit(qc, LoweringOptions(tile_bits=5, max_high=2))
+    assert np.max(np.abs(run_program(low, psi0) - want)) < 1e-12
+    assert low.n_passes == 1 and low.pass_info[0].fixed_bits == 1
+    assert low.pass_bytes(0) == 2 * 16 * 2**9
+    assert low.amp_updates() == 2 * 2**9
+
+
+def test_sharded_index_offset_semantics():
+    # rank bits enter only through index_offset: run the two halves of an 8-qubit state as two
+    # 7-qubit shards for a circuit whose top qubit is only used as control / in diagonals
+    rng = np.random.default_rng(9)
+    from _util import random_unitary
+    from qls_b200.circuit import Gate
+    n = 8
+    qc = QuantumCircuit(n)
+    for q in range(n - 1):
+        qc.h(q)
+        qc.cp(0.3 * (q + 1), n - 1, q)
+    qc.append(Gate("unitary", 2, [], random_unitary(2, rng)).control(1), [n - 1, 2, 5])
+    qc.rz(0.7, n - 1)
+    psi0 = rng.standard_normal(2**n) + 1j * rng.standard_normal(2**n)
+    psi0 /= np.linalg.norm(psi0)
+    want = numpy_sv.run(n, circuit_to_stream(qc), psi0=psi0)
+    low = lower_circuit(qc, LoweringOptions(tile_bits=5, max_high=2, n_local=n - 1))
+    half = 2 ** (n - 1)
+    got = np.concatenate([run_program(low, psi0[:half], 0), run_program(low, psi0[half:], half)])
+    assert np.max(np.abs(got - want)) < 1e-12
