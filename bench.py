@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: HHL-shaped statevector solves on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--qubits n] [--impl reference]
+
+One *step* = one full solve of the synthetic HHL-shaped circuit (BASELINE.json configs[3] at
+N = 1: QPE + uniformly-controlled RY + inverse QPE, 33 qubits fp64 = 128 GiB state; configs[4] =
+the same circuit at 33 + log2(N) qubits sharded over N GPUs): state preparation, every fused tile
+pass, the reductions P(flag=1) and |x|^2.  metric = amplitude updates per second (sum over fused
+blocks of 2^(n-c)) for the whole job.
+
+Prints ONE JSON line (see the task contract): value (device-timed, inputs resident in HBM), e2e
+(host buffers in and out through ShapedSolver.solve), roofline (tile-pass kernel vs measured HBM
+peak), cpu_baseline (oracle/numpy_sv.py = the reference's qiskit Statevector algorithm restated,
+on a bounded smaller instance of the same circuit), clocks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hhl_amp_updates_per_s"
+UNIT = "amp-updates/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline: the oracle (restated qiskit Statevector path) on a bounded instance
+# ------------------------------------------------------------------------------------------------
+
+
+def cpu_reference_sample(n_cpu: int, repeats: int = 1):
+    """Time the unfused leaf stream of the HHL-shaped circuit at ``n_cpu`` qubits through
+    ``oracle.numpy_sv`` (reshape/transpose/np.dot per gate).  Returns (amp_updates, seconds)."""
+    from oracle import numpy_sv
+    from oracle.stream import leaves_to_stream
+    from qls_b200.circuit import flatten
+    from qls_b200.lower import LoweringOptions, lower_circuit
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    qc = hhl_shaped_circuit(n_cpu)
+    leaves, phase = flatten(qc)
+    stream = leaves_to_stream(leaves, phase)
+    job = lower_circuit(qc, LoweringOptions(dtype="fp64")).amp_updates()  # same job definition as the GPU arm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        psi = numpy_sv.run(n_cpu, stream)
+        half = psi.size // 2
+        _ = numpy_sv.prob_mask(psi, half, half), float(abs(psi[half: half + 2 ** ((n_cpu - 1) // 2)] ** 2).sum())
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return job, best, len(leaves)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = args.cpu_qubits
+    times = []
+    job = leaves = 0
+    for i in range(args.warmup + args.steps):
+        job, dt, leaves = cpu_reference_sample(n_cpu)
+        if i >= args.warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    value = job / sec
+    cores = os.cpu_count() or 1
+    sample = (f"HHL-shaped circuit at n={n_cpu} qubits fp64 ({leaves} unfused leaf gates, one reshape/transpose/np.dot "
+              f"pass each = qiskit Statevector._evolve_operator restated in oracle/numpy_sv.py); BLAS threads default")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"hhl_shaped_n{n_cpu}_cpu_sample_of_n{args.qubits or 33}", "n_qubits": n_cpu},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+
+def pick_qubits(requested: int, free_bytes: int) -> int:
+    if requested:
+        return requested
+    n = 33
+    while n > 20 and (16 << n) + (6 << 30) > free_bytes:
+        n -= 1
+    return n
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 through torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    from qls_b200.lower import LoweringOptions
+    from qls_b200.solver_shaped import ShapedSolver
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    free_bytes, _total = torch.cuda.mem_get_info()
+    if world > 1:
+        from qls_b200.shard import ShardedShapedSolver  # sharded states: 33 + log2(N) qubits
+
+        n = args.qubits or (pick_qubits(0, free_bytes) + int(np.log2(world)))
+        qc = hhl_shaped_circuit(n)
+        nb = qc.qregs[0].size
+        solver = ShardedShapedSolver(qc, nb, precision=args.precision, device=local_rank)
+    else:
+        n = pick_qubits(args.qubits, free_bytes)
+        qc = hhl_shaped_circuit(n)
+        nb = qc.qregs[0].size
+        solver = ShapedSolver(qc, nb, precision=args.precision, device=local_rank)
+    low = solver.lowered
+    amp_updates = solver.amp_updates_global() if world > 1 else low.amp_updates()
+    S = low.amp_bytes()
+
+    rng = np.random.default_rng(99)
+    b = rng.standard_normal(2**nb) + 0j
+    b /= np.linalg.norm(b)
+    cdt = torch.complex128 if args.precision == "fp64" else torch.complex64
+    b_pinned = torch.from_numpy(b).to(cdt).pin_memory()
+    b_dev = b_pinned.to(f"cuda:{local_rank}")
+    b_host = b_pinned.numpy()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        solver.run_device(b_dev)
+        return solver.reduce()
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+
+    # ---- timed: device-resident inputs ----------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    last = None
+    for _ in range(args.steps):
+        last = device_step()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- timed: tile-pass kernels alone (roofline numerator), CUDA events on the launch stream --
+    kern_ms, kern_launches, kern_bytes = solver.time_passes(args.steps)
+
+    # ---- timed: end to end, host buffers in and out --------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        x, p_flag, norm_sq = solver.solve(b_host)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([dev_ms, e2e_ms, kern_ms or 0.0], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, kern_ms = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        n_tile = low.n_passes
+        pass_bytes = low.total_pass_bytes()
+        roofline = None
+        if kern_ms:
+            achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "qls_tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                        "launches_per_step": kern_launches, "algorithmic_bytes_per_step": kern_bytes,
+                        "avg_launch_ms": kern_ms / max(1, kern_launches), "kernel_ms_per_step": kern_ms}
+        # CPU baseline on a bounded sample of the same workload
+        job_cpu, sec_cpu, leaves = cpu_reference_sample(args.cpu_qubits)
+        cpu = {"value": job_cpu / sec_cpu, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"same circuit at n={args.cpu_qubits} ({leaves} unfused leaf gates through oracle/numpy_sv.py, "
+                         f"{sec_cpu:.2f} s); per-amplitude cost is size independent"}
+        launches_per_step = solver.program.launches_per_run + 2 + 4  # + init fill/copy + two 2-kernel reductions
+        line = {
+            "metric": METRIC, "value": amp_updates / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
+            "config": {"workload": f"hhl_shaped_n{n}" + (f"_sharded_{world}gpu" if world > 1 else ""),
+                       "n_qubits": n, "nb": nb, "nl": n - 1 - nb, "state_bytes_per_gpu": S << low.n_local,
+                       "fused_passes": n_tile, "fused_blocks": int(sum(p.n_ops for p in low.pass_info)),
+                       "source_gates": low.n_source_gates, "amp_updates_per_step": amp_updates,
+                       "hbm_bytes_per_step": pass_bytes + (S << low.n_local),
+                       "l2_policy": "inputs_larger_than_L2" if (S << low.n_local) > (256 << 20) else "state_fits_L2_no_flush",
+                       "program": "lowered once outside the timed region; b differs per solve only through init"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": amp_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(b_host.nbytes), "d2h_bytes_per_step": int(x.nbytes) + 2 * 16,
+                    "api": "ShapedSolver.solve(b_host) -> (x_host, P(flag=1), |x|^2)"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "result_check": {"p_flag1": last[0], "norm_sq": last[1], "e2e_p_flag1": p_flag},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=0, help="total qubits (default: 33 on 1 GPU if it fits)")
+    ap.add_argument("--cpu-qubits", type=int, default=23, help="size of the bounded CPU sample")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

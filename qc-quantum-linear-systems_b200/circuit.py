@@ -726,20 +726,34 @@ def _leaf_of(op: Gate, qubits: Tuple[int, ...]) -> Optional[Leaf]:
     return Leaf("dense", qubits, m, controls, ctrl_state, base.name)
 
 
-def flatten(circuit: QuantumCircuit) -> Tuple[List[Leaf], float]:
+def flatten(circuit: QuantumCircuit, parametric: bool = False) -> Tuple[List[Leaf], float]:
     """Leaf stream + accumulated global phase, walking definitions exactly as
     ``Statevector._evolve_instruction`` does: a gate with a matrix is
     applied as is, otherwise ``definition.global_phase`` is multiplied in and the definition is
-    walked with remapped qubit arguments."""
+    walked with remapped qubit arguments.
+
+    With ``parametric=True`` unbound ``ry/rx/rz/p`` gates become ``"param"`` leaves whose payload
+    is ``(gate name, parameter index, coeff, offset)`` -- the index is the parameter's position in
+    ``circuit.parameters`` (the order ``Estimator.run`` binds ``parameter_values`` in)."""
     leaves: List[Leaf] = []
     phase = [float(circuit.global_phase)]
+    pindex = {id(p): i for i, p in enumerate(circuit.parameters)} if parametric else {}
 
-    def walk(c: QuantumCircuit, qmap: Sequence[int], ctrls: Tuple[int, ...], cstate: int) -> None:
+    def walk(c: QuantumCircuit, qmap: Sequence[int]) -> None:
         for ins in c.data:
             op = ins.operation
             qs = tuple(qmap[q] for q in ins.qubits)
-            if op.is_parameterized:
-                raise ValueError(f"circuit has unbound parameters (gate {op.name!r})")
+            base = op.base_gate if isinstance(op, ControlledGate) else op
+            if any(_is_free(p) for p in base.params):
+                if not parametric:
+                    raise ValueError(f"circuit has unbound parameters (gate {op.name!r})")
+                if base.name not in ("ry", "rx", "rz", "p"):
+                    raise NotImplementedError(f"parameterised {base.name!r} gates are not supported")
+                expr = base.params[0]
+                nc = op.num_ctrl_qubits if isinstance(op, ControlledGate) else 0
+                leaves.append(Leaf("param", qs[nc:], (base.name, pindex[id(expr.parameter)], expr.coeff, expr.offset),
+                                   qs[:nc], op.ctrl_state if nc else 0, base.name))
+                continue
             leaf = _leaf_of(op, qs)
             if leaf is not None:
                 leaves.append(leaf)
@@ -747,7 +761,7 @@ def flatten(circuit: QuantumCircuit) -> Tuple[List[Leaf], float]:
             if op.definition is None:
                 raise ValueError(f"gate {op.name!r} has neither a matrix nor a definition")
             phase[0] += op.definition.global_phase
-            walk(op.definition, qs, ctrls, cstate)
+            walk(op.definition, qs)
 
-    walk(circuit, list(range(circuit.num_qubits)), (), 0)
+    walk(circuit, list(range(circuit.num_qubits)))
     return leaves, phase[0]

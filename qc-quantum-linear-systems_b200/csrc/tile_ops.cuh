@@ -13,21 +13,21 @@ __device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp&
   constexpr int D = 1 << K;
   constexpr int R = D / S;
   const int gbits = T - K;
-  const int nitems = (1 << gbits) * S;
+  const int ngroups = 1 << gbits;
+  constexpr int GPI = THREADS / S;  // groups per iteration: all S row slices of a group run together
   uint32_t bit[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) bit[j] = 1u << op.tq[j];
   const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+  const int h = tid / GPI;  // row slice (warp-uniform)
 
-  for (int it0 = 0; it0 < nitems; it0 += THREADS) {
-    const int item = it0 + tid;
-    bool active = item < nitems;
+  for (int g0 = 0; g0 < ngroups; g0 += GPI) {
+    const int g = g0 + (tid % GPI);
+    bool active = g < ngroups;
     uint32_t idx = 0;
-    int h = 0;
     V acc[R];
     if (active) {
-      h = item >> gbits;
-      idx = item & ((1 << gbits) - 1);
+      idx = g;
 #pragma unroll
       for (int j = 0; j < K; ++j) idx = insert_zero_bit(idx, op.tq[j]);
       active = (idx & lc_mask) == lc_val;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp&
         sm[idx | off] = acc[r];
       }
     }
-    if (S > 1 && it0 + THREADS < nitems) __syncthreads();
+    if (S > 1 && g0 + GPI < ngroups) __syncthreads();
   }
 }
 

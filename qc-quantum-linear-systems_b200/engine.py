@@ -161,12 +161,13 @@ class DeviceProgram:
         with torch.cuda.device(self.device):
             stream = _stream_ptr()
             first = 0
-            if initialise:
-                if steps and steps[0].kind == "init":
+            if steps and steps[0].kind == "init":
+                # initialise=False: the caller has already prepared the register (e.g. another b)
+                if initialise:
                     self._run_init(state, steps[0])
-                    first = 1
-                else:
-                    state.init_basis(0 if state.index_offset == 0 else None)
+                first = 1
+            elif initialise:
+                state.init_basis(0 if state.index_offset == 0 else None)
             for i in range(first, len(steps)):
                 s = steps[i]
                 if s.kind == "passes":
@@ -182,6 +183,38 @@ class DeviceProgram:
                     raise NotImplementedError("state preparation is only supported as the first operation")
                 else:
                     raise ValueError(s.kind)
+
+    def run_passes_timed(self, state: DeviceState):
+        """Run every step after the state preparation with CUDA events (on the launching stream)
+        around each contiguous range of tile passes.  Returns (tile-pass ms, tile-pass launches,
+        algorithmic bytes of those launches); other steps run untimed."""
+        torch = _torch()
+        lw = self.lowered
+        pairs = []
+        launches = 0
+        nbytes = 0
+        with torch.cuda.device(self.device):
+            stream = _stream_ptr()
+            for i, s in enumerate(lw.steps):
+                if s.kind == "init":
+                    continue
+                if s.kind == "passes":
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    _abi.check(self.lib.qls_program_run(self.handle, state.ptr, state.n_local, state.index_offset,
+                                                        s.pass_begin, s.pass_end, stream))
+                    b.record()
+                    pairs.append((a, b))
+                    launches += s.pass_end - s.pass_begin
+                    nbytes += sum(lw.pass_bytes(j, state.n_local) for j in range(s.pass_begin, s.pass_end))
+                elif s.kind == "gemm":
+                    n_rows_sel = 2 ** (state.n_local - s.nb - bin(s.ctrl_mask & (2**state.n_local - 1)).count("1"))
+                    scratch = state.scratch(n_rows_sel * 2**s.nb)
+                    _abi.check(self.lib.qls_ctrl_gemm(state.ptr, scratch.data_ptr(), state.n_local, self.abi_dtype, s.nb,
+                                                      s.ctrl_mask, s.ctrl_val, state.index_offset,
+                                                      self._gemm_mats[i].data_ptr(), stream))
+            torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in pairs), launches, nbytes
 
     def _run_init(self, state: DeviceState, s: Step) -> None:
         k = len(s.qubits)

@@ -64,6 +64,37 @@ def test_random_circuits_tile_shapes(cuda_device, seed, tile, high, fuse):
     assert np.max(np.abs(got - want)) <= TOL64
 
 
+@pytest.mark.parametrize("tile,high,fuse", [(6, 3, 2), (13, 5, 5), (13, 6, 3), (12, 5, 4)])
+def test_random_circuits_tile_shapes_fp32(cuda_device, tile, high, fuse):
+    rng = np.random.default_rng(2500 + tile + high)
+    n = 15
+    qc = random_circuit(n, 50, rng, max_k=min(5, high))
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = _gpu_state(qc, precision="fp32", tile_bits=tile, max_high=high, max_fuse_qubits=fuse).data
+    assert np.max(np.abs(got - want)) <= TOL32
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_k5_dense_blocks_in_large_tiles(cuda_device, precision):
+    """k = 5 dense blocks use two threads per amplitude group; cover tiles with more groups than
+    one sweep of the CTA handles (13-bit tiles) and controls inside / outside the tile."""
+    from qls_b200.circuit import Gate, QuantumCircuit
+
+    rng = np.random.default_rng(31)
+    n = 16
+    qc = QuantumCircuit(n)
+    for q in range(n):
+        qc.h(q)
+    for _ in range(6):
+        qs = [int(q) for q in rng.choice(n, 6, replace=False)]
+        qc.append(Gate("unitary", 5, [], random_unitary(5, rng)).control(1, int(rng.integers(2))), qs)
+        qc.unitary(random_unitary(5, rng), [int(q) for q in rng.choice(n, 5, replace=False)])
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    for tile in (12, 13):
+        got = _gpu_state(qc, precision=precision, tile_bits=tile, max_high=5).data
+        assert np.max(np.abs(got - want)) <= (TOL64 if precision == "fp64" else TOL32)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_random_circuits_fp32(cuda_device, seed):
     rng = np.random.default_rng(3000 + seed)
