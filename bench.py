@@ -239,6 +239,18 @@ def run_gpu(args):
 
     # ---- timed: tile-pass kernels alone (roofline numerator), CUDA events on the launch stream --
     kern_ms, kern_launches, kern_bytes = solver.time_passes(args.steps)
+    if args.profile_passes and rank == 0 and world == 1:
+        solver.state.init_basis(None)
+        solver.state.write(0, b_host)
+        per = solver.program.run_each_pass_timed(solver.state)
+        for j, ms in per:
+            pi = low.pass_info[j]
+            ps = low.passes[j]
+            recs = [low.ops[t] for t in range(ps.op_begin, ps.op_begin + ps.op_count)]
+            sweeps = [(r.kind, r.k) for r in recs if not (r.flags & 12)]
+            gbs = low.pass_bytes(j) / (ms * 1e-3) / 1e9
+            print(f"pass {j:3d} {ms:9.3f} ms {gbs:8.1f} GB/s L={pi.low_bits} high={pi.high} fix={pi.fixed_bits} "
+                  f"recs={pi.n_ops} sweeps={sweeps}", file=sys.stderr)
 
     # ---- timed: end to end, host buffers in and out --------------------------------------------
     barrier()
@@ -311,6 +323,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=0, help="total qubits (default: 33 on 1 GPU if it fits)")
     ap.add_argument("--cpu-qubits", type=int, default=23, help="size of the bounded CPU sample")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--profile-passes", action="store_true", help="print per-pass timings to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -47,6 +47,12 @@ enum {
 #define QLS_MAX_FSEG 16
 #define QLS_OP_FLAG_REAL 1u  /* DENSE matrix is real (imaginary parts are zero) */
 #define QLS_OP_FLAG_PARAM 2u /* batch kernel only: a k=1 RY whose angle comes from the parameter array */
+/* A DIAG record flagged ATTACH_* is not an operation of its own: it rides on the closest preceding
+ * un-flagged record (its host: an unconditional DENSE, or a DIAG) and is applied to the host's
+ * inputs (PRE) or outputs (POST) while they are in registers -- no extra shared-memory sweep. */
+#define QLS_OP_FLAG_ATTACH_PRE 4u
+#define QLS_OP_FLAG_ATTACH_POST 8u
+#define QLS_MAX_ATTACH 4
 
 /* bit-field gather: ((x >> src) & ((1 << width) - 1)) << dst */
 typedef struct QlsSeg {

@@ -4,12 +4,63 @@
 #pragma once
 #include "qls_common.cuh"
 
+// ---- attached diagonal tables ------------------------------------------------------------------------
+// Diagonal runs next to an unconditional dense block are applied to that block's inputs / outputs
+// while they sit in registers (QLS_OP_FLAG_ATTACH_*), so the tile is swept once instead of twice or
+// three times.  `Att` caches what is uniform for the tile: table pointers and the part of each table
+// index that comes from index bits outside the tile.
+template <typename V>
+struct Att {
+  int n;
+  uint32_t pre_mask;  // bit a set: attachment a applies to inputs, else to outputs
+  const V* table[QLS_MAX_ATTACH];
+  uint32_t xidx[QLS_MAX_ATTACH];
+  const QlsOp* rec;
+};
+
+template <typename V>
+__device__ __forceinline__ Att<V> make_att(const QlsOp* __restrict__ rec, int n, const unsigned char* __restrict__ pool,
+                                           uint64_t gbase) {
+  Att<V> a;
+  a.n = n;
+  a.rec = rec;
+  a.pre_mask = 0;
+#pragma unroll
+  for (int i = 0; i < QLS_MAX_ATTACH; ++i) {
+    if (i < n) {
+      a.table[i] = reinterpret_cast<const V*>(pool + rec[i].pool_off);
+      a.xidx[i] = (uint32_t)gather_segs64(gbase, rec[i].xseg, rec[i].n_xseg);
+      if (rec[i].flags & QLS_OP_FLAG_ATTACH_PRE) a.pre_mask |= 1u << i;
+    }
+  }
+  return a;
+}
+
+// product of the attached tables of one side (PRE / POST) at tile-local index i
+template <typename V, bool PRE>
+__device__ __forceinline__ V att_apply(const Att<V>& a, uint32_t i, V v) {
+#pragma unroll
+  for (int t = 0; t < QLS_MAX_ATTACH; ++t) {
+    if (t < a.n && (((a.pre_mask >> t) & 1u) != 0) == PRE) {
+      const QlsOp& r = a.rec[t];
+      uint32_t ti = a.xidx[t];
+      const int nl = r.n_lseg;
+#pragma unroll
+      for (int s = 0; s < QLS_MAX_SEG; ++s)
+        if (s < nl) ti |= ((i >> r.lseg[s].src) & ((1u << r.lseg[s].width) - 1u)) << r.lseg[s].dst;
+      v = cmul(v, __ldg(&a.table[t][ti]));
+    }
+  }
+  return v;
+}
+
 // ---- DENSE: 2^K x 2^K matrix on K tile-local qubits ----------------------------------------------
 // One work item = (group of 2^K amplitudes, slice of R = 2^K / S output rows).  Inputs are streamed
 // from shared memory, the R accumulators live in registers, outputs are written once all reads of
 // the group are done (S > 1 needs a block barrier for that; S == 1 does not).
 template <typename V, int K, int S, int THREADS, bool REAL>
-__device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ M, int tid) {
+__device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ M, int tid,
+                                         const Att<V>& att) {
   constexpr int D = 1 << K;
   constexpr int R = D / S;
   const int gbits = T - K;
@@ -20,6 +71,8 @@ __device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp&
   for (int j = 0; j < K; ++j) bit[j] = 1u << op.tq[j];
   const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
   const int h = tid / GPI;  // row slice (warp-uniform)
+  const bool has_pre = att.pre_mask != 0;
+  const bool has_post = att.n > 0 && att.pre_mask != ((1u << att.n) - 1u);
 
   for (int g0 = 0; g0 < ngroups; g0 += GPI) {
     const int g = g0 + (tid % GPI);
@@ -41,7 +94,8 @@ __device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp&
         uint32_t off = 0;
 #pragma unroll
         for (int j = 0; j < K; ++j) off |= ((c >> j) & 1) ? bit[j] : 0u;
-        const V v = sm[idx | off];
+        V v = sm[idx | off];
+        if (has_pre) v = att_apply<V, true>(att, idx | off, v);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const V m = __ldg(&Mrow[(r << K) | c]);
@@ -62,22 +116,21 @@ __device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp&
         uint32_t off = 0;
 #pragma unroll
         for (int j = 0; j < K; ++j) off |= ((row >> j) & 1) ? bit[j] : 0u;
-        sm[idx | off] = acc[r];
+        V o = acc[r];
+        if (has_post) o = att_apply<V, false>(att, idx | off, o);
+        sm[idx | off] = o;
       }
     }
     if (S > 1 && g0 + GPI < ngroups) __syncthreads();
   }
 }
 
-// ---- DIAG: amp *= table[bits of the (global) index] -----------------------------------------------
+// ---- DIAG: amp *= table[bits of the (global) index] (times any attached tables) --------------------
 template <typename V, int THREADS>
 __device__ __forceinline__ void op_diag(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ table,
-                                        uint64_t gbase, int tid) {
+                                        uint64_t gbase, int tid, const Att<V>& att) {
   const uint32_t xidx = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg);
   const int nl = op.n_lseg;
-  QlsSeg ls[QLS_MAX_SEG];
-#pragma unroll
-  for (int i = 0; i < QLS_MAX_SEG; ++i) ls[i] = op.lseg[i];
   const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
   const int n = 1 << T;
   for (int i = tid; i < n; i += THREADS) {
@@ -85,8 +138,10 @@ __device__ __forceinline__ void op_diag(V* __restrict__ sm, int T, const QlsOp& 
     uint32_t ti = xidx;
 #pragma unroll
     for (int s = 0; s < QLS_MAX_SEG; ++s)
-      if (s < nl) ti |= ((i >> ls[s].src) & ((1u << ls[s].width) - 1u)) << ls[s].dst;
-    sm[i] = cmul(sm[i], __ldg(&table[ti]));
+      if (s < nl) ti |= ((i >> op.lseg[s].src) & ((1u << op.lseg[s].width) - 1u)) << op.lseg[s].dst;
+    V v = cmul(sm[i], __ldg(&table[ti]));
+    if (att.n) v = att_apply<V, false>(att, i, v);
+    sm[i] = v;
   }
 }
 
@@ -96,9 +151,6 @@ __device__ __forceinline__ void op_muxry(V* __restrict__ sm, int T, const QlsOp&
                                          uint64_t gbase, int tid) {
   const uint32_t xidx = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg);
   const int nl = op.n_lseg;
-  QlsSeg ls[QLS_MAX_SEG];
-#pragma unroll
-  for (int i = 0; i < QLS_MAX_SEG; ++i) ls[i] = op.lseg[i];
   const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
   const uint32_t tq = op.tq[0];
   const int n = 1 << (T - 1);
@@ -108,7 +160,7 @@ __device__ __forceinline__ void op_muxry(V* __restrict__ sm, int T, const QlsOp&
     uint32_t ti = xidx;
 #pragma unroll
     for (int s = 0; s < QLS_MAX_SEG; ++s)
-      if (s < nl) ti |= ((i0 >> ls[s].src) & ((1u << ls[s].width) - 1u)) << ls[s].dst;
+      if (s < nl) ti |= ((i0 >> op.lseg[s].src) & ((1u << op.lseg[s].width) - 1u)) << op.lseg[s].dst;
     const V cs = __ldg(&table[ti]);
     const uint32_t i1 = i0 | (1u << tq);
     const V a0 = sm[i0], a1 = sm[i1];
@@ -128,40 +180,51 @@ __device__ __forceinline__ void op_muxry(V* __restrict__ sm, int T, const QlsOp&
 template <typename V, int THREADS, bool HEAVY>
 __device__ __forceinline__ void apply_ops(V* __restrict__ sm, int T, const QlsOp* __restrict__ ops, int n_ops,
                                           const unsigned char* __restrict__ pool, uint64_t gbase, int tid) {
-  for (int o = 0; o < n_ops; ++o) {
+  int o = 0;
+  while (o < n_ops) {
     const QlsOp& op = ops[o];
-    if ((gbase & op.xc_mask) != op.xc_val) continue;  // block-uniform
+    int n_att = 0;
+    while (n_att < QLS_MAX_ATTACH && o + 1 + n_att < n_ops &&
+           (ops[o + 1 + n_att].flags & (QLS_OP_FLAG_ATTACH_PRE | QLS_OP_FLAG_ATTACH_POST)))
+      ++n_att;
+    const int next = o + 1 + n_att;
+    if ((gbase & op.xc_mask) != op.xc_val) {  // block-uniform
+      o = next;
+      continue;
+    }
     const V* data = reinterpret_cast<const V*>(pool + op.pool_off);
     const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
+    const Att<V> att = make_att<V>(ops + o + 1, n_att, pool, gbase);
     switch (op.kind) {
       case QLS_OP_DENSE:
         switch (op.k) {
           case 1:
-            if (real) op_dense<V, 1, 1, THREADS, true>(sm, T, op, data, tid);
-            else op_dense<V, 1, 1, THREADS, false>(sm, T, op, data, tid);
+            if (real) op_dense<V, 1, 1, THREADS, true>(sm, T, op, data, tid, att);
+            else op_dense<V, 1, 1, THREADS, false>(sm, T, op, data, tid, att);
             break;
           case 2:
-            if (real) op_dense<V, 2, 1, THREADS, true>(sm, T, op, data, tid);
-            else op_dense<V, 2, 1, THREADS, false>(sm, T, op, data, tid);
+            if (real) op_dense<V, 2, 1, THREADS, true>(sm, T, op, data, tid, att);
+            else op_dense<V, 2, 1, THREADS, false>(sm, T, op, data, tid, att);
             break;
           case 3:
-            op_dense<V, 3, 1, THREADS, false>(sm, T, op, data, tid);
+            op_dense<V, 3, 1, THREADS, false>(sm, T, op, data, tid, att);
             break;
           case 4:
-            if (HEAVY) op_dense<V, 4, 1, THREADS, false>(sm, T, op, data, tid);
+            if (HEAVY) op_dense<V, 4, 1, THREADS, false>(sm, T, op, data, tid, att);
             break;
           case 5:
-            if (HEAVY) op_dense<V, 5, 2, THREADS, false>(sm, T, op, data, tid);
+            if (HEAVY) op_dense<V, 5, 2, THREADS, false>(sm, T, op, data, tid, att);
             break;
         }
         break;
       case QLS_OP_DIAG:
-        op_diag<V, THREADS>(sm, T, op, data, gbase, tid);
+        op_diag<V, THREADS>(sm, T, op, data, gbase, tid, att);
         break;
       case QLS_OP_MUXRY:
         op_muxry<V, THREADS>(sm, T, op, data, gbase, tid);
         break;
     }
     __syncthreads();
+    o = next;
   }
 }

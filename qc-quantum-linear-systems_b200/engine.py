@@ -184,6 +184,25 @@ class DeviceProgram:
                 else:
                     raise ValueError(s.kind)
 
+    def run_each_pass_timed(self, state: DeviceState):
+        """Debug aid: per-pass milliseconds (one CUDA event pair per tile pass)."""
+        torch = _torch()
+        lw = self.lowered
+        out = []
+        with torch.cuda.device(self.device):
+            stream = _stream_ptr()
+            for s in lw.steps:
+                if s.kind != "passes":
+                    continue
+                for j in range(s.pass_begin, s.pass_end):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    _abi.check(self.lib.qls_program_run(self.handle, state.ptr, state.n_local, state.index_offset, j, j + 1, stream))
+                    b.record()
+                    out.append((j, a, b))
+            torch.cuda.synchronize()
+        return [(j, a.elapsed_time(b)) for j, a, b in out]
+
     def run_passes_timed(self, state: DeviceState):
         """Run every step after the state preparation with CUDA events (on the launching stream)
         around each contiguous range of tile passes.  Returns (tile-pass ms, tile-pass launches,

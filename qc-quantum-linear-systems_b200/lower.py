@@ -97,8 +97,15 @@ def normalise(leaves: Sequence[Leaf], max_dense: int = 5) -> List[Block]:
         if lf.kind == "init":
             out.append(Block("init", tuple(lf.targets), amps=np.asarray(lf.payload, dtype=complex)))
         elif lf.kind == "diag":
-            qs, tab = _fold_controls_diag(tuple(lf.targets), np.asarray(lf.payload, dtype=complex), ctrl)
-            out.append(Block("diag", qs, factors=[(qs, tab)]))
+            tab = np.asarray(lf.payload, dtype=complex)
+            if ctrl and len(lf.targets) >= 3:
+                # a controlled diagonal *sub-circuit* (e.g. the phase run inside a controlled
+                # e^{iAt} block): keep the controls symbolic so that a pass whose blocks all share
+                # them can skip the other half of the tiles
+                out.append(Block("diag", tuple(lf.targets), dict(ctrl), factors=[(tuple(lf.targets), tab)]))
+            else:
+                qs, tab = _fold_controls_diag(tuple(lf.targets), tab, ctrl)
+                out.append(Block("diag", qs, factors=[(qs, tab)]))
         elif lf.kind == "ucry":
             tgt, sel = lf.targets[0], tuple(lf.targets[1:])
             ang = np.asarray(lf.payload, dtype=float)
@@ -174,69 +181,106 @@ def _expand_dense(b: Block, qubits: Tuple[int, ...]) -> np.ndarray:
     return full
 
 
+def _fold_diag_block(b: Block) -> Block:
+    """Diagonal block with its symbolic controls folded into the tables."""
+    if not b.controls:
+        return b
+    factors = []
+    for fq, ft in b.factors:
+        q2, t2 = _fold_controls_diag(tuple(fq), ft, b.controls)
+        factors.append((q2, t2))
+    qs = tuple(sorted(set(b.targets) | set(b.controls)))
+    return Block("diag", qs, factors=factors, n_source=b.n_source)
+
+
 def fuse(blocks: Sequence[Block], max_fuse_qubits: int = 3, max_diag_qubits: int = 10,
          max_mux_selectors: int = 20) -> List[Block]:
+    """Greedy peephole fusion.  For every incoming block the *earliest legal position* ``pos`` is
+    found by scanning back over blocks it commutes with; it may then be merged into any
+    compatible block at or after ``pos`` (diagonals, RY multiplexers) or into the block that stops
+    it (small dense gates), or it is inserted at ``pos`` (1-qubit gates -- this is what lets the
+    QFT's later phase ladders merge into earlier tables) or appended."""
     out: List[Block] = []
     for b in blocks:
+        if b.kind in ("init", "gemm"):
+            out.append(b)
+            continue
+        pos = 0
+        for i in range(len(out) - 1, -1, -1):
+            prev = out[i]
+            if prev.kind in ("init", "gemm") or not _commutes(prev, b):
+                if not (prev.kind == "muxry" and b.kind == "muxry" and prev.targets == b.targets):
+                    pos = i + 1
+                    break
+        blocker = out[pos - 1] if pos > 0 else None
+
         if b.kind == "diag":
-            merged = False
-            for prev in reversed(out):
-                if prev.kind == "diag":
+            done = False
+            for i in range(pos, len(out)):
+                prev = out[i]
+                if prev.kind != "diag":
+                    continue
+                if prev.controls == b.controls:
                     union = set(prev.targets) | set(b.targets)
-                    if len(union) <= max_diag_qubits:
+                    if len(union) + len(prev.controls) <= max_diag_qubits:
                         prev.targets = tuple(sorted(union))
                         prev.factors = prev.factors + b.factors
                         prev.n_source += b.n_source
-                        merged = True
-                    break
-                if not _commutes(prev, b):
-                    break
-            if not merged:
-                out.append(Block("diag", tuple(sorted(b.targets)), factors=list(b.factors), n_source=b.n_source))
+                        done = True
+                        break
+                else:
+                    fp, fb = _fold_diag_block(prev), _fold_diag_block(b)
+                    union = set(fp.targets) | set(fb.targets)
+                    if len(union) <= max_diag_qubits:
+                        out[i] = Block("diag", tuple(sorted(union)), factors=fp.factors + fb.factors,
+                                       n_source=prev.n_source + b.n_source)
+                        done = True
+                        break
+            if not done:
+                out.append(Block("diag", tuple(sorted(b.targets)), dict(b.controls), factors=list(b.factors),
+                                 n_source=b.n_source))
             continue
+
         if b.kind == "muxry":
-            merged = False
-            for prev in reversed(out):
+            done = False
+            for i in range(pos, len(out)):
+                prev = out[i]
                 if prev.kind == "muxry" and prev.targets == b.targets:
                     union = list(prev.selectors) + [q for q in b.selectors if q not in prev.selectors]
                     if len(union) <= max_mux_selectors:
                         prev.angles = _mux_expand(prev.angles, prev.selectors, union) + _mux_expand(b.angles, b.selectors, union)
                         prev.selectors = tuple(union)
                         prev.n_source += b.n_source
-                        merged = True
-                    break
-                if not _commutes(prev, b):
-                    break
-            if not merged:
+                        done = True
+                        break
+            if not done:
                 out.append(Block("muxry", b.targets, selectors=b.selectors, angles=np.array(b.angles), n_source=b.n_source))
             continue
-        if b.kind == "dense":
-            cand = None
-            for prev in reversed(out):
-                if _commutes(prev, b):
-                    continue
-                cand = prev
-                break
-            if cand is not None and cand.kind == "dense":
-                union = tuple(sorted(cand.support | b.support))
-                small = len(b.support) <= 2 and len(cand.support) <= max_fuse_qubits
-                tunion = tuple(sorted(set(cand.targets) | set(b.targets)))
-                if cand.controls == b.controls and len(tunion) <= max(max_fuse_qubits, len(cand.targets), len(b.targets)):
-                    # same controls: multiply the target matrices, keep the controls symbolic
-                    ma = _expand_dense(Block("dense", cand.targets, {}, cand.matrix), tunion)
-                    mb = _expand_dense(Block("dense", b.targets, {}, b.matrix), tunion)
-                    cand.targets, cand.matrix = tunion, mb @ ma
-                    cand.n_source += b.n_source
-                    continue
-                if small and len(union) <= max_fuse_qubits:
-                    ma = _expand_dense(cand, union)
-                    mb = _expand_dense(b, union)
-                    cand.targets, cand.controls, cand.matrix = union, {}, mb @ ma
-                    cand.n_source += b.n_source
-                    continue
-            out.append(Block("dense", b.targets, dict(b.controls), b.matrix, n_source=b.n_source))
-            continue
-        out.append(b)
+
+        # dense
+        cand = blocker
+        if cand is not None and cand.kind == "dense":
+            union = tuple(sorted(cand.support | b.support))
+            small = len(b.support) <= 2 and len(cand.support) <= max_fuse_qubits
+            tunion = tuple(sorted(set(cand.targets) | set(b.targets)))
+            if cand.controls == b.controls and len(tunion) <= max(max_fuse_qubits, len(cand.targets), len(b.targets)):
+                # same controls: multiply the target matrices, keep the controls symbolic
+                ma = _expand_dense(Block("dense", cand.targets, {}, cand.matrix), tunion)
+                mb = _expand_dense(Block("dense", b.targets, {}, b.matrix), tunion)
+                cand.targets, cand.matrix = tunion, mb @ ma
+                cand.n_source += b.n_source
+                continue
+            if small and len(union) <= max_fuse_qubits:
+                ma = _expand_dense(cand, union)
+                mb = _expand_dense(b, union)
+                cand.targets, cand.controls, cand.matrix = union, {}, mb @ ma
+                cand.n_source += b.n_source
+                continue
+        nb_ = Block("dense", b.targets, dict(b.controls), b.matrix, n_source=b.n_source)
+        if len(b.targets) == 1 and not b.controls and pos < len(out) and all(o.kind == "diag" for o in out[pos:]):
+            out.insert(pos, nb_)  # hop over trailing diagonal tables it commutes with
+        else:
+            out.append(nb_)
     # a fused dense block may have become diagonal or the identity
     final: List[Block] = []
     for b in out:
@@ -248,6 +292,39 @@ def fuse(blocks: Sequence[Block], max_fuse_qubits: int = 3, max_diag_qubits: int
         else:
             final.append(b)
     return final
+
+
+def tensor_merge(blocks: Sequence[Block], max_fuse_qubits: int = 3) -> List[Block]:
+    """Tensor-product fusion inside one pass: an unconditional 1-2 qubit gate is multiplied into
+    an earlier unconditional small gate it can reach by commutation -- one shared-memory sweep
+    instead of two for the same traffic.  FP64 cost model: a complex k=2 or a real k=3 block is
+    still balanced against the sweep's shared-memory time, so those are the caps."""
+    out: List[Block] = []
+    for b in blocks:
+        if b.kind == "dense" and not b.controls and len(b.targets) <= 2:
+            pos = 0
+            for i in range(len(out) - 1, -1, -1):
+                if not _commutes(out[i], b):
+                    pos = i + 1
+                    break
+            b_real = not np.any(b.matrix.imag)
+            merged = False
+            for i in range(pos, len(out)):
+                prev = out[i]
+                if prev.kind != "dense" or prev.controls:
+                    continue
+                tunion = tuple(sorted(set(prev.targets) | set(b.targets)))
+                both_real = b_real and not np.any(prev.matrix.imag)
+                if len(tunion) <= min(max_fuse_qubits, 3 if both_real else 2):
+                    ma = _expand_dense(prev, tunion)
+                    mb = _expand_dense(b, tunion)
+                    out[i] = Block("dense", tunion, {}, mb @ ma, n_source=prev.n_source + b.n_source)
+                    merged = True
+                    break
+            if merged:
+                continue
+        out.append(b)
+    return out
 
 
 def _mux_expand(angles: np.ndarray, sel: Sequence[int], union: Sequence[int]) -> np.ndarray:
@@ -427,7 +504,7 @@ class _Emitter:
     def flush(self) -> None:
         if not self.cur:
             return
-        blocks, self.cur = self.cur, []
+        blocks, self.cur = tensor_merge(self.cur, self.opts.max_fuse_qubits), []
         needed = set(self.cur_high)
         self.cur_high = set()
         T = self.T
@@ -443,7 +520,8 @@ class _Emitter:
         # pass-level controls: external control bits shared by every op (tile skipping)
         common: Optional[Dict[int, int]] = None
         for b in blocks:
-            ext = {q: v for q, v in b.controls.items() if q not in local_pos and q < self.n_local} if b.kind == "dense" else {}
+            ext = ({q: v for q, v in b.controls.items() if q not in local_pos and q < self.n_local}
+                   if b.kind in ("dense", "diag") else {})
             common = ext if common is None else {q: v for q, v in common.items() if ext.get(q) == v}
         common = common or {}
         fix_mask = sum(1 << q for q in common)
@@ -453,12 +531,53 @@ class _Emitter:
         op_controls: List[int] = []
         heavy = False
         n_source = 0
+        # Diagonal tables ride on a neighbouring unconditional dense block (applied to its inputs /
+        # outputs in registers) or are chained onto one another: one tile sweep per host.
+        pending: List[_abi.QlsOp] = []  # tables waiting for a host
+        host_room = 0  # attachments the last emitted host can still take (0: no open host)
+
+        def flush_pending() -> None:
+            nonlocal host_room
+            while pending:
+                head = pending.pop(0)
+                self.ops.append(head)
+                take = pending[:_abi.QLS_MAX_ATTACH]
+                del pending[:_abi.QLS_MAX_ATTACH]
+                for t in take:
+                    t.flags |= _abi.QLS_OP_FLAG_ATTACH_POST
+                    self.ops.append(t)
+            host_room = 0
+
         for b in blocks:
             n_source += b.n_source
-            for op, nctrl in self._emit_block(b, local_pos, T):
+            op_controls.append(len(b.controls))
+            if b.kind == "diag":
+                bb = b if all(q in common for q in b.controls) else _fold_diag_block(b)
+                for op, _ in self._emit_block(bb, local_pos, T):
+                    if host_room > 0:
+                        op.flags |= _abi.QLS_OP_FLAG_ATTACH_POST
+                        self.ops.append(op)
+                        host_room -= 1
+                    else:
+                        pending.append(op)
+                continue
+            unconditional = b.kind == "dense" and all(q in common for q in b.controls)
+            if unconditional:
+                keep = pending[-_abi.QLS_MAX_ATTACH:]
+                del pending[-_abi.QLS_MAX_ATTACH:]
+                flush_pending()
+                (op, _), = self._emit_block(b, local_pos, T)
                 self.ops.append(op)
-                op_controls.append(nctrl)
-                heavy |= op.kind == _abi.QLS_OP_DENSE and op.k >= 4
+                for t in keep:
+                    t.flags |= _abi.QLS_OP_FLAG_ATTACH_PRE
+                    self.ops.append(t)
+                host_room = _abi.QLS_MAX_ATTACH - len(keep)
+            else:
+                flush_pending()
+                for op, _ in self._emit_block(b, local_pos, T):
+                    self.ops.append(op)
+            heavy |= b.kind == "dense" and len(b.targets) >= 4
+        flush_pending()
 
         p = _abi.QlsPass()
         p.tile_bits, p.low_bits, p.n_high = T, L, len(high_sorted)

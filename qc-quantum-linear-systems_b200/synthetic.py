@@ -2,9 +2,11 @@
 
 Same structure as ``HHL.construct_circuit`` -- state preparation, QPE (H layer, one controlled
 block per clock qubit, inverse QFT without swaps, bit-reversed), ``ExactReciprocal``, inverse QPE
--- but the controlled ``e^{iAt 2^j}`` of clock qubit ``j`` is a seeded random 5-qubit unitary on
-data qubits followed by a random diagonal phase run, because a dense ``2^nb x 2^nb`` matrix stops
-being representable long before the state stops fitting in HBM."""
+-- but the controlled ``e^{iAt 2^j}`` of clock qubit ``j`` is a seeded Trotter-like step: a chain
+of Haar-random two-qubit unitaries over five data qubits followed by a random diagonal phase run
+on six, because a dense ``2^nb x 2^nb`` matrix stops being representable long before the state
+stops fitting in HBM.  (``block="dense5"`` replaces the chain by one Haar-random five-qubit
+unitary: 256 flop per 32 bytes, beyond the FP64 ridge of a B200 -- kept as a stress case.)"""
 from __future__ import annotations
 
 import numpy as np
@@ -23,7 +25,8 @@ def haar_unitary(k: int, rng: np.random.Generator) -> np.ndarray:
 class SyntheticEvolution:
     """Stand-in for ``NumPyMatrix``: ``power(2**j)`` is block ``j``."""
 
-    def __init__(self, num_qubits: int, num_blocks: int, seed: int = 2024, dense_qubits: int = 5, diag_qubits: int = 6):
+    def __init__(self, num_qubits: int, num_blocks: int, seed: int = 2024, dense_qubits: int = 5, diag_qubits: int = 6,
+                 block: str = "chain2"):
         self.num_qubits = self.num_state_qubits = num_qubits
         self.num_ancillas = 0
         self._blocks = []
@@ -33,18 +36,26 @@ class SyntheticEvolution:
             kg = min(diag_qubits, num_qubits)
             dq = sorted(int(q) for q in rng.choice(num_qubits, kd, replace=False))
             gq = sorted(int(q) for q in rng.choice(num_qubits, kg, replace=False))
-            self._blocks.append((dq, haar_unitary(kd, rng), gq, np.exp(1j * rng.uniform(-np.pi, np.pi, 2**kg))))
+            if block == "dense5" or kd < 2:
+                gates = [(dq, haar_unitary(kd, rng))]
+            elif block == "chain2":
+                gates = [([dq[i], dq[i + 1]], haar_unitary(2, rng)) for i in range(kd - 1)]
+            else:
+                raise ValueError(block)
+            self._blocks.append((gates, gq, np.exp(1j * rng.uniform(-np.pi, np.pi, 2**kg))))
 
     def power(self, power: int) -> QuantumCircuit:
         j = int(round(np.log2(power)))
-        dq, u, gq, d = self._blocks[j]
+        gates, gq, d = self._blocks[j]
         qc = QuantumCircuit(self.num_qubits, name=f"U**{power}")
-        qc.unitary(u, dq)
+        for qs, u in gates:
+            qc.unitary(u, qs)
         qc.diagonal(d, gq)
         return qc
 
 
-def hhl_shaped_circuit(num_qubits: int, seed: int = 2024, b_seed: int = 99, nb: int = 0) -> QuantumCircuit:
+def hhl_shaped_circuit(num_qubits: int, seed: int = 2024, b_seed: int = 99, nb: int = 0,
+                       block: str = "chain2") -> QuantumCircuit:
     """``num_qubits = nb + nl + 1``; default split ``nb = (n-1)//2`` (n = 33 -> nb = nl = 16)."""
     n = int(num_qubits)
     nb = nb or (n - 1) // 2
@@ -60,7 +71,7 @@ def hhl_shaped_circuit(num_qubits: int, seed: int = 2024, b_seed: int = 99, nb: 
     prep = QuantumCircuit(nb, name="isometry")
     prep.prepare_state(b, list(range(nb)))
     qc.append(prep.to_gate(), qb_q)
-    qpe = PhaseEstimation(nl, SyntheticEvolution(nb, nl, seed))
+    qpe = PhaseEstimation(nl, SyntheticEvolution(nb, nl, seed, block=block))
     qc.append(qpe.to_gate(), ql_q + qb_q)
     delta = 2.0 ** (-(nl // 2))
     qc.append(ExactReciprocal(nl, delta, neg_vals=True).to_gate(), ql_q[::-1] + [qf_q[0]])

@@ -38,7 +38,25 @@ def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0):
     sm = state[G]  # tiles x 2^T
     gbase = base | index_offset
     esz = np.dtype(cdtype).itemsize
-    for o in range(p.op_begin, p.op_begin + p.op_count):
+    ATT = _abi.QLS_OP_FLAG_ATTACH_PRE | _abi.QLS_OP_FLAG_ATTACH_POST
+    order = []  # execution order: PRE attachments, host, POST attachments
+    o = p.op_begin
+    end = p.op_begin + p.op_count
+    while o < end:
+        assert not (ops[o].flags & ATT), "attachment without a host"
+        att = []
+        while len(att) < _abi.QLS_MAX_ATTACH and o + 1 + len(att) < end and (ops[o + 1 + len(att)].flags & ATT):
+            att.append(o + 1 + len(att))
+        if att:
+            host = ops[o]
+            assert host.kind in (_abi.QLS_OP_DENSE, _abi.QLS_OP_DIAG) and host.lc_mask == 0
+            assert all(ops[a].kind == _abi.QLS_OP_DIAG and ops[a].lc_mask == 0 and ops[a].xc_mask == 0 for a in att)
+            if host.kind == _abi.QLS_OP_DIAG:
+                assert all(ops[a].flags & _abi.QLS_OP_FLAG_ATTACH_POST for a in att)
+        order += [a for a in att if ops[a].flags & _abi.QLS_OP_FLAG_ATTACH_PRE] + [o]
+        order += [a for a in att if ops[a].flags & _abi.QLS_OP_FLAG_ATTACH_POST]
+        o += 1 + len(att)
+    for o in order:
         op = ops[o]
         act = (gbase & op.xc_mask) == op.xc_val
         if not act.any():
