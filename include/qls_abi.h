@@ -39,14 +39,16 @@ enum { QLS_OK = 0, QLS_ERR_ARG = 1, QLS_ERR_CUDA = 2, QLS_ERR_UNSUPPORTED = 3, Q
 enum {
   QLS_OP_DENSE = 1, /* 2^k x 2^k complex matrix on k tile qubits (k <= 5), optional controls   */
   QLS_OP_DIAG = 2,  /* merged diagonal run: amp *= table[index bits]                          */
-  QLS_OP_MUXRY = 3  /* uniformly controlled RY: (cos, sin) table selected by index bits       */
+  QLS_OP_MUXRY = 3, /* uniformly controlled RY: (cos, sin) table selected by index bits       */
+  QLS_OP_MATVEC = 4 /* batch kernel only: dense 2^k x 2^k on k contiguous tile qubits tq[0]..   */
 };
 
 #define QLS_MAX_SEG 6
 #define QLS_MAX_HIGH 8
 #define QLS_MAX_FSEG 16
 #define QLS_OP_FLAG_REAL 1u  /* DENSE matrix is real (imaginary parts are zero) */
-#define QLS_OP_FLAG_PARAM 2u /* batch kernel only: a k=1 RY whose angle comes from the parameter array */
+#define QLS_OP_FLAG_PARAM 2u /* batch kernel only: a 1-qubit rotation whose angle comes from the parameter
+                              * array; pad0 selects the gate: 0 ry, 1 rx, 2 rz, 3 p */
 /* A DIAG record flagged ATTACH_* is not an operation of its own: it rides on the closest preceding
  * un-flagged record (its host: an unconditional DENSE, or a DIAG) and is applied to the host's
  * inputs (PRE) or outputs (POST) while they are in registers -- no extra shared-memory sweep. */
@@ -72,7 +74,7 @@ typedef struct QlsOp {
   uint8_t n_lseg;     /* DIAG/MUXRY: table index fields taken from the tile-local index       */
   uint8_t n_xseg;     /*             ... and from the tile's global base index                */
   uint8_t flags;
-  uint8_t pad0;
+  uint8_t pad0;       /* QLS_OP_FLAG_PARAM: rotation kind                                     */
   uint32_t pad1;
   QlsSeg lseg[QLS_MAX_SEG];
   QlsSeg xseg[QLS_MAX_SEG];

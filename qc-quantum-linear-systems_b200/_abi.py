@@ -8,7 +8,8 @@ import os
 from typing import Optional
 
 QLS_C128, QLS_C64 = 0, 1
-QLS_OP_DENSE, QLS_OP_DIAG, QLS_OP_MUXRY = 1, 2, 3
+QLS_OP_DENSE, QLS_OP_DIAG, QLS_OP_MUXRY, QLS_OP_MATVEC = 1, 2, 3, 4
+PARAM_KINDS = {"ry": 0, "rx": 1, "rz": 2, "p": 3}
 QLS_MAX_SEG, QLS_MAX_HIGH, QLS_MAX_FSEG = 6, 8, 16
 QLS_OP_FLAG_REAL, QLS_OP_FLAG_PARAM = 1, 2
 QLS_OP_FLAG_ATTACH_PRE, QLS_OP_FLAG_ATTACH_POST, QLS_MAX_ATTACH = 4, 8, 4

@@ -1,7 +1,199 @@
-// Batched small-circuit kernel (VQLS Hadamard tests) -- placeholder until the kernel lands.
-#include "qls_common.cuh"
+// Batched small-circuit kernel: one CTA evolves one whole statevector (n <= 12 qubits in fp64,
+// 13 in fp32) in shared memory and reduces <Z_q> -- the Hadamard tests that VQLS sends through
+// Estimator.run (reference call site vqls_qiskit_implementation.py:55-62; SURVEY.md 8a rows
+// a10/a11).  All circuits of a launch share one op program; what differs per circuit is the
+// parameter vector theta[circuit][*] that the QLS_OP_FLAG_PARAM rotations read.
+//
+// The in-tile op implementations are the ones of the streaming kernel (tile_ops.cuh); added here:
+//   * PARAM   : ry / rx / rz / p with angle = coeff * theta[param_index] + offset (optionally controlled)
+//   * MATVEC  : a dense 2^k x 2^k unitary on k contiguous qubits (k up to n), out of place into a
+//               second shared-memory buffer -- the controlled A_i / U_b^dagger blocks.
+#include "tile_ops.cuh"
 
-extern "C" int qls_batch_expect_z(const QlsProgram*, uint32_t, int, int, const double*, uint32_t, uint32_t, double*, void*) {
-  qls_set_error("qls_batch_expect_z: not built yet");
-  return QLS_ERR_UNSUPPORTED;
+enum { PARAM_RY = 0, PARAM_RX = 1, PARAM_RZ = 2, PARAM_P = 3 };
+
+template <typename V, typename R, int THREADS>
+__device__ __forceinline__ void op_param(V* __restrict__ sm, int T, const QlsOp& op, R angle, int tid) {
+  V m00, m01, m10, m11;
+  R s, c;
+  sincos(angle * R(0.5), &s, &c);
+  switch (op.pad0) {
+    case PARAM_RY:
+      m00 = {c, 0}; m01 = {-s, 0}; m10 = {s, 0}; m11 = {c, 0};
+      break;
+    case PARAM_RX:
+      m00 = {c, 0}; m01 = {0, -s}; m10 = {0, -s}; m11 = {c, 0};
+      break;
+    case PARAM_RZ:
+      m00 = {c, -s}; m01 = {0, 0}; m10 = {0, 0}; m11 = {c, s};
+      break;
+    default: {  // P(angle) = diag(1, e^{i angle})
+      R s1, c1;
+      sincos(angle, &s1, &c1);
+      m00 = {1, 0}; m01 = {0, 0}; m10 = {0, 0}; m11 = {c1, s1};
+    }
+  }
+  const uint32_t tq = op.tq[0];
+  const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+  const int n = 1 << (T - 1);
+  for (int g = tid; g < n; g += THREADS) {
+    const uint32_t i0 = insert_zero_bit(g, tq);
+    if ((i0 & lc_mask) != lc_val) continue;
+    const uint32_t i1 = i0 | (1u << tq);
+    const V a0 = sm[i0], a1 = sm[i1];
+    V b0 = cmul(m00, a0), b1 = cmul(m10, a0);
+    cfma(b0, m01, a1);
+    cfma(b1, m11, a1);
+    sm[i0] = b0;
+    sm[i1] = b1;
+  }
+}
+
+// out[o | r << lo] = sum_c U[r][c] in[o | c << lo] for every outer index o whose controls hold;
+// other amplitudes are copied.  One warp per output row r, lanes stride the columns (coalesced
+// 512-byte reads of the U row), shuffle reduction; up to 4 outer indices share each U read.
+template <typename V, int THREADS>
+__device__ __forceinline__ void op_matvec(const V* __restrict__ in, V* __restrict__ out, int T, const QlsOp& op,
+                                          const V* __restrict__ U, int tid) {
+  const int k = op.k, lo = op.tq[0];
+  const int D = 1 << k;
+  const int n_outer = 1 << (T - k);
+  const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = THREADS / 32;
+  for (int i = tid; i < (1 << T); i += THREADS) out[i] = in[i];
+  __syncthreads();
+  for (int ob = 0; ob < n_outer; ob += 4) {
+    uint32_t base[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t o = ob + j;
+      // deposit the outer counter around the k target bits
+      base[j] = ((o >> lo) << (lo + k)) | (o & ((1u << lo) - 1u));
+      ok[j] = (o < (uint32_t)n_outer) && ((base[j] & lc_mask) == lc_val);
+    }
+    if (!(ok[0] || ok[1] || ok[2] || ok[3])) continue;
+    for (int r = warp; r < D; r += NW) {
+      V acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j].x = acc[j].y = 0;
+      for (int c = lane; c < D; c += 32) {
+        const V u = __ldg(&U[(size_t)r * D + c]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ok[j]) cfma(acc[j], u, in[base[j] | ((uint32_t)c << lo)]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, s);
+          acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, s);
+        }
+        if (lane == 0 && ok[j]) out[base[j] | ((uint32_t)r << lo)] = acc[j];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <typename R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    qls_batch_expect_z_kernel(const QlsOp* __restrict__ ops, int n_ops, const unsigned char* __restrict__ pool, int n,
+                              int z_qubit, const double* __restrict__ params, int n_params, int two_buffers,
+                              double* __restrict__ out) {
+  using V = typename Vec2<R>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* cur = reinterpret_cast<V*>(smem_raw);
+  V* alt = cur + ((size_t)1 << n);
+  const int tid = threadIdx.x;
+  const int dim = 1 << n;
+  const double* theta = params + (size_t)blockIdx.x * n_params;
+
+  for (int i = tid; i < dim; i += THREADS) {
+    V z;
+    z.x = (i == 0) ? R(1) : R(0);
+    z.y = 0;
+    cur[i] = z;
+  }
+  __syncthreads();
+
+  int o = 0;
+  while (o < n_ops) {
+    const QlsOp& op = ops[o];
+    if (op.kind == QLS_OP_DENSE && (op.flags & QLS_OP_FLAG_PARAM)) {
+      const R angle = (R)((double)op.param_coeff * theta[op.param_index] + (double)op.param_offset);
+      op_param<V, R, THREADS>(cur, n, op, angle, tid);
+      __syncthreads();
+      ++o;
+    } else if (op.kind == QLS_OP_MATVEC) {
+      if (two_buffers) {
+        op_matvec<V, THREADS>(cur, alt, n, op, reinterpret_cast<const V*>(pool + op.pool_off), tid);
+        V* t = cur;
+        cur = alt;
+        alt = t;
+      }
+      ++o;
+    } else {  // maximal run of streaming-kernel ops
+      int e = o + 1;
+      while (e < n_ops && !(ops[e].kind == QLS_OP_MATVEC) &&
+             !(ops[e].kind == QLS_OP_DENSE && (ops[e].flags & QLS_OP_FLAG_PARAM)))
+        ++e;
+      apply_ops<V, THREADS, true>(cur, n, ops + o, e - o, pool, 0ull, tid);
+      o = e;
+    }
+  }
+
+  // <Z_q> = sum_i (-1)^{bit_q(i)} |psi_i|^2
+  double s = 0.0;
+  for (int i = tid; i < dim; i += THREADS) {
+    const V v = cur[i];
+    const double p = (double)v.x * v.x + (double)v.y * v.y;
+    s += ((i >> z_qubit) & 1) ? -p : p;
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  __shared__ double wsum[THREADS / 32];
+  if ((tid & 31) == 0) wsum[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < THREADS / 32; ++w) t += wsum[w];
+    out[blockIdx.x] = t;
+  }
+}
+
+extern "C" int qls_batch_expect_z(const QlsProgram* prog, uint32_t pass_index, int n_qubits, int z_qubit,
+                                  const double* params_dev, uint32_t n_circuits, uint32_t n_params, double* out_dev,
+                                  void* stream) {
+  QLS_ARG(prog && out_dev, "null program / output");
+  QLS_ARG(pass_index < prog->n_passes, "pass index %u outside program", pass_index);
+  QLS_ARG(n_params == 0 || params_dev, "null parameter array");
+  const QlsPass& p = prog->passes_host[pass_index];
+  QLS_ARG(p.tile_bits == n_qubits && p.n_high == 0 && p.fix_mask == 0, "batch programs need one whole-state pass");
+  QLS_ARG(z_qubit >= 0 && z_qubit < n_qubits, "observable qubit outside the circuit");
+  const int max_n = prog->dtype == QLS_C128 ? 12 : 13;
+  QLS_ARG(n_qubits >= 1 && n_qubits <= max_n, "batch kernel supports 1..%d qubits, got %d", max_n, n_qubits);
+  if (n_circuits == 0) return QLS_OK;
+  QLS_CUDA(cudaSetDevice(prog->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int two = (p.pad & 2u) ? 1 : 0;  // set by qls_program_create when the pass holds a MATVEC
+  const size_t esz = prog->dtype == QLS_C128 ? 16 : 8;
+  const size_t smem = (esz << n_qubits) * (two ? 2 : 1);
+  QLS_ARG(smem <= 200 * 1024, "state does not fit shared memory (%zu bytes)", smem);
+  constexpr int THREADS = 256;
+  if (prog->dtype == QLS_C128) {
+    auto kern = qls_batch_expect_z_kernel<double, THREADS>;
+    QLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kern<<<n_circuits, THREADS, smem, s>>>(prog->ops_dev + p.op_begin, (int)p.op_count, prog->pool_dev, n_qubits, z_qubit,
+                                           params_dev, (int)n_params, two, out_dev);
+  } else {
+    auto kern = qls_batch_expect_z_kernel<float, THREADS>;
+    QLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kern<<<n_circuits, THREADS, smem, s>>>(prog->ops_dev + p.op_begin, (int)p.op_count, prog->pool_dev, n_qubits, z_qubit,
+                                           params_dev, (int)n_params, two, out_dev);
+  }
+  QLS_CUDA(cudaGetLastError());
+  return QLS_OK;
 }

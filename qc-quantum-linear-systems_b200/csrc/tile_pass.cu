@@ -119,6 +119,7 @@ extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local,
     const QlsPass& p = prog->passes_host[i];
     int rc = validate_pass(p, n_local, prog->dtype);
     if (rc) return rc;
+    QLS_ARG(!(p.pad & 4u), "pass %u holds batch-only ops (PARAM / MATVEC): use qls_batch_expect_z", i);
     bool heavy = (p.pad & 1u) != 0;  // set by qls_program_create when the pass holds a k >= 4 dense op
     if (prog->dtype == QLS_C128)
       rc = heavy ? launch_pass<double, true>(prog, p, state, n_local, index_offset, s)
@@ -141,10 +142,15 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   const size_t esz = dtype == QLS_C128 ? 16 : 8;
   for (uint32_t i = 0; i < n_ops; ++i) {
     const QlsOp& op = ops_host[i];
-    QLS_ARG(op.kind >= QLS_OP_DENSE && op.kind <= QLS_OP_MUXRY, "op %u: bad kind %d", i, op.kind);
+    QLS_ARG(op.kind >= QLS_OP_DENSE && op.kind <= QLS_OP_MATVEC, "op %u: bad kind %d", i, op.kind);
     QLS_ARG(op.n_lseg <= QLS_MAX_SEG && op.n_xseg <= QLS_MAX_SEG, "op %u: too many segments", i);
     QLS_ARG(op.pool_off % esz == 0 && op.pool_off < pool_bytes + (pool_bytes == 0), "op %u: bad pool offset", i);
-    if (op.kind == QLS_OP_DENSE) {
+    if (op.kind == QLS_OP_MATVEC) {
+      QLS_ARG(op.k >= 1 && op.k <= 13, "op %u: matvec k=%d unsupported", i, op.k);
+      QLS_ARG(op.pool_off + (esz << (2 * op.k)) <= pool_bytes, "op %u: matrix outside pool", i);
+    } else if (op.kind == QLS_OP_DENSE && (op.flags & QLS_OP_FLAG_PARAM)) {
+      QLS_ARG(op.k == 1 && op.pad0 <= 3, "op %u: bad parameterised rotation", i);
+    } else if (op.kind == QLS_OP_DENSE) {
       QLS_ARG(op.k >= 1 && op.k <= 5, "op %u: dense k=%d unsupported", i, op.k);
       QLS_ARG(op.pool_off + (esz << (2 * op.k)) <= pool_bytes, "op %u: matrix outside pool", i);
       for (int j = 1; j < op.k; ++j) QLS_ARG(op.tq[j] > op.tq[j - 1], "op %u: targets not ascending", i);
@@ -168,10 +174,12 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
       delete p;
       return QLS_ERR_ARG;
     }
-    bool heavy = false;
+    bool heavy = false, matvec = false, batch_only = false;
     for (uint32_t o = ps.op_begin; o < ps.op_begin + ps.op_count; ++o) {
       const QlsOp& op = ops_host[o];
       if (op.kind == QLS_OP_DENSE && op.k >= 4) heavy = true;
+      if (op.kind == QLS_OP_MATVEC) matvec = batch_only = true;
+      if (op.kind == QLS_OP_DENSE && (op.flags & QLS_OP_FLAG_PARAM)) batch_only = true;
       for (int j = 0; j < (op.kind == QLS_OP_DIAG ? 0 : op.k); ++j)
         if (op.tq[j] >= ps.tile_bits) {
           qls_set_error("pass %u op %u: target bit %d outside tile of %d bits", i, o, (int)op.tq[j], ps.tile_bits);
@@ -180,7 +188,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
           return QLS_ERR_ARG;
         }
     }
-    ps.pad = heavy ? 1u : 0u;
+    ps.pad = (heavy ? 1u : 0u) | (matvec ? 2u : 0u) | (batch_only ? 4u : 0u);
   }
   cudaError_t e = cudaSuccess;
   if (n_ops) {

@@ -43,12 +43,13 @@ class Block:
     selectors: Tuple[int, ...] = ()  # muxry: table-bit order
     angles: Optional[np.ndarray] = None  # muxry
     amps: Optional[np.ndarray] = None  # init
+    param: Optional[Tuple[str, int, float, float]] = None  # param: (gate, parameter index, coeff, offset)
     n_source: int = 1  # leaf gates folded into this block
 
     @property
     def touched(self) -> frozenset:
         """Qubits acted on non-diagonally."""
-        if self.kind in ("dense", "gemm", "init"):
+        if self.kind in ("dense", "gemm", "init", "param"):
             return frozenset(self.targets)
         if self.kind == "muxry":
             return frozenset(self.targets[:1])
@@ -90,11 +91,13 @@ def _fold_controls_diag(qubits: Tuple[int, ...], table: np.ndarray, controls: Di
     return qubits + cq, full
 
 
-def normalise(leaves: Sequence[Leaf], max_dense: int = 5) -> List[Block]:
+def normalise(leaves: Sequence[Leaf], max_dense: int = 5, batch: bool = False) -> List[Block]:
     out: List[Block] = []
     for lf in leaves:
         ctrl = {q: (lf.ctrl_state >> j) & 1 for j, q in enumerate(lf.controls)}
-        if lf.kind == "init":
+        if lf.kind == "param":
+            out.append(Block("param", tuple(lf.targets), ctrl, param=tuple(lf.payload)))
+        elif lf.kind == "init":
             out.append(Block("init", tuple(lf.targets), amps=np.asarray(lf.payload, dtype=complex)))
         elif lf.kind == "diag":
             tab = np.asarray(lf.payload, dtype=complex)
@@ -129,14 +132,16 @@ def normalise(leaves: Sequence[Leaf], max_dense: int = 5) -> List[Block]:
             elif k <= max_dense:
                 out.append(Block("dense", tuple(lf.targets), ctrl, m))
             else:
-                order = np.argsort(lf.targets)
-                if sorted(lf.targets) != list(range(k)):
+                lo = min(lf.targets)
+                want = list(range(lo, lo + k))
+                if sorted(lf.targets) != want or (lo != 0 and not batch):
                     raise NotImplementedError(
-                        f"dense {k}-qubit block must act on the low qubits 0..{k-1} (GEMM block); got {lf.targets}"
+                        f"dense {k}-qubit block must act on contiguous qubits"
+                        f"{'' if batch else ' 0..' + str(k - 1)} (GEMM block); got {lf.targets}"
                     )
-                if list(order) != list(range(k)):
-                    m = _permute_matrix(m, [lf.targets.index(q) for q in range(k)])
-                out.append(Block("gemm", tuple(range(k)), ctrl, m))
+                if list(lf.targets) != want:
+                    m = _permute_matrix(m, [lf.targets.index(q) for q in want])
+                out.append(Block("gemm", tuple(want), ctrl, m))
         else:
             raise ValueError(lf.kind)
     return out
@@ -202,7 +207,7 @@ def fuse(blocks: Sequence[Block], max_fuse_qubits: int = 3, max_diag_qubits: int
     QFT's later phase ladders merge into earlier tables) or appended."""
     out: List[Block] = []
     for b in blocks:
-        if b.kind in ("init", "gemm"):
+        if b.kind in ("init", "gemm", "param"):
             out.append(b)
             continue
         pos = 0
@@ -350,6 +355,7 @@ class LoweringOptions:
     max_fuse_qubits: int = 3
     max_diag_qubits: int = 10
     n_local: int = 0  # 0 -> all qubits local (single GPU)
+    batch: bool = False  # one whole-state pass for qls_batch_expect_z (parameterised, n <= 12/13)
 
     def resolved_tile_bits(self) -> int:
         return self.tile_bits or (12 if self.dtype == "fp64" else 13)
@@ -438,8 +444,8 @@ class _Emitter:
         self.n = n
         self.opts = opts
         self.n_local = opts.n_local or n
-        self.T = min(opts.resolved_tile_bits(), self.n_local)
-        self.Hmax = min(opts.max_high, self.T)
+        self.T = self.n_local if opts.batch else min(opts.resolved_tile_bits(), self.n_local)
+        self.Hmax = 0 if opts.batch else min(opts.max_high, self.T)
         self.Lmin = self.T - self.Hmax
         if opts.dtype == "fp32" and self.Lmin < 1:
             self.Lmin = min(1, self.T)
@@ -481,6 +487,12 @@ class _Emitter:
         return None
 
     def add(self, b: Block) -> None:
+        if self.opts.batch:
+            if b.kind == "init":
+                raise NotImplementedError("state preparation inside a batched circuit")
+            self.cur.append(b)
+            self.cur_high |= set(b.touched)
+            return
         if b.kind in ("init", "gemm"):
             self.flush()
             if b.kind == "init":
@@ -639,6 +651,23 @@ class _Emitter:
             op.pool_off = self._pool_add(m)
             self._controls(op, b.controls, local_pos)
             yield op, len(b.controls)
+        elif b.kind == "param":
+            name, pidx, coeff, offset = b.param
+            op = _abi.QlsOp()
+            op.kind, op.k = _abi.QLS_OP_DENSE, 1
+            op.flags |= _abi.QLS_OP_FLAG_PARAM
+            op.pad0 = _abi.PARAM_KINDS[name]
+            op.tq[0] = local_pos[b.targets[0]]
+            op.param_index, op.param_coeff, op.param_offset = int(pidx), float(coeff), float(offset)
+            self._controls(op, b.controls, local_pos)
+            yield op, len(b.controls)
+        elif b.kind == "gemm":
+            op = _abi.QlsOp()
+            op.kind, op.k = _abi.QLS_OP_MATVEC, len(b.targets)
+            op.tq[0] = local_pos[b.targets[0]]
+            op.pool_off = self._pool_add(b.matrix)
+            self._controls(op, b.controls, local_pos)
+            yield op, len(b.controls)
         elif b.kind == "muxry":
             op = _abi.QlsOp()
             op.kind, op.k = _abi.QLS_OP_MUXRY, 1
@@ -710,12 +739,12 @@ def lower_blocks(num_qubits: int, blocks: Sequence[Block], opts: LoweringOptions
 def lower_leaves(num_qubits: int, leaves: Sequence[Leaf], global_phase: float = 0.0,
                  opts: Optional[LoweringOptions] = None, fused: bool = True) -> LoweredProgram:
     opts = opts or LoweringOptions()
-    blocks = normalise(leaves)
+    blocks = normalise(leaves, batch=opts.batch)
     if fused:
         blocks = fuse(blocks, opts.max_fuse_qubits, opts.max_diag_qubits)
     return lower_blocks(num_qubits, blocks, opts, global_phase, n_source_gates=len(leaves))
 
 
 def lower_circuit(circuit: QuantumCircuit, opts: Optional[LoweringOptions] = None, fused: bool = True) -> LoweredProgram:
-    leaves, phase = flatten(circuit)
+    leaves, phase = flatten(circuit, parametric=bool(opts and opts.batch))
     return lower_leaves(circuit.num_qubits, leaves, phase, opts, fused)

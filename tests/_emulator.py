@@ -23,7 +23,7 @@ def _insert_zero(x, pos):
     return ((x >> pos) << (pos + 1)) | low
 
 
-def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0):
+def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0, params=None):
     T, L = p.tile_bits, p.low_bits
     fixed = bin(p.fix_mask).count("1")
     free_bits = n_local - T - fixed
@@ -61,9 +61,26 @@ def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0):
         act = (gbase & op.xc_mask) == op.xc_val
         if not act.any():
             continue
-        if op.kind == _abi.QLS_OP_DENSE:
+        if op.kind == _abi.QLS_OP_MATVEC:
+            K, lo = op.k, op.tq[0]
+            U = np.frombuffer(pool, dtype=cdtype, count=4**K, offset=op.pool_off).reshape(2**K, 2**K)
+            outer = np.arange(2 ** (T - K), dtype=np.int64)
+            base_o = ((outer >> lo) << (lo + K)) | (outer & ((1 << lo) - 1))
+            base_o = base_o[(base_o & op.lc_mask) == op.lc_val]
+            cols = base_o[:, None] | (np.arange(2**K, dtype=np.int64) << lo)[None, :]
+            sub = sm[:, cols]  # tiles x outer x 2^K
+            sm[:, cols] = np.einsum("rc,toc->tor", U, sub).astype(cdtype)
+        elif op.kind == _abi.QLS_OP_DENSE:
             K = op.k
-            M = np.frombuffer(pool, dtype=cdtype, count=4**K, offset=op.pool_off).reshape(2**K, 2**K)
+            if op.flags & _abi.QLS_OP_FLAG_PARAM:
+                ang = float(np.float32(op.param_coeff)) * params[op.param_index] + float(np.float32(op.param_offset))
+                c_, s_ = np.cos(ang / 2), np.sin(ang / 2)
+                M = {0: np.array([[c_, -s_], [s_, c_]], dtype=complex),
+                     1: np.array([[c_, -1j * s_], [-1j * s_, c_]]),
+                     2: np.diag([np.exp(-0.5j * ang), np.exp(0.5j * ang)]),
+                     3: np.diag([1, np.exp(1j * ang)])}[op.pad0].astype(cdtype)
+            else:
+                M = np.frombuffer(pool, dtype=cdtype, count=4**K, offset=op.pool_off).reshape(2**K, 2**K)
             g = np.arange(2 ** (T - K), dtype=np.int64)
             idx = g.copy()
             for j in range(K):
@@ -114,7 +131,7 @@ def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0):
     _ = esz
 
 
-def run_program(lowered, psi0=None, index_offset=0):
+def run_program(lowered, psi0=None, index_offset=0, params=None):
     """Evolve |0...0> (or ``psi0``) through a LoweredProgram; returns the final local state."""
     n = lowered.n_local
     cdtype = np.complex128 if lowered.dtype == "fp64" else np.complex64
@@ -133,7 +150,7 @@ def run_program(lowered, psi0=None, index_offset=0):
     for s in steps:
         if s.kind == "passes":
             for pi in range(s.pass_begin, s.pass_end):
-                run_pass(state, lowered.passes[pi], lowered.ops, pool, cdtype, n, index_offset)
+                run_pass(state, lowered.passes[pi], lowered.ops, pool, cdtype, n, index_offset, params)
         elif s.kind == "gemm":
             nb = s.nb
             rows = np.arange(2 ** (n - nb), dtype=np.int64)

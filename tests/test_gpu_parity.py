@@ -254,3 +254,83 @@ def test_large_state_properties(cuda_device, precision, tol):
     back = st.read(0, 2**nb)
     assert np.max(np.abs(back - b)) < tol * 10
     assert abs(st.norm_sq_range(0, 2**nb) - 1.0) < tol * 10
+
+
+# ---- VQLS path: batched estimator kernel ---------------------------------------------------------
+
+
+@pytest.mark.parametrize("nq,precision", [(1, "fp64"), (2, "fp64"), (3, "fp64"), (3, "fp32")])
+def test_estimator_matches_oracle_on_hadamard_tests(cuda_device, nq, precision):
+    """Estimator.run values (reference call site vqls_qiskit_implementation.py:55-62) vs bind +
+    oracle + <Z_0>, for every Hadamard-test circuit VQLS builds, 8 parameter vectors per launch."""
+    from qls_b200.estimator import B200Estimator
+    from qls_b200.library import RealAmplitudes
+    from qls_b200.vqls import VQLS
+
+    rng = np.random.default_rng(40 + nq)
+    dim = 2**nq
+    a = rng.standard_normal((dim, dim))
+    a = a + a.T
+    b = rng.standard_normal(dim)
+    ansatz = RealAmplitudes(nq, reps=3)
+    vq = VQLS(None, ansatz, None)
+    norm_t, over_t = vq.construct_circuit(a, b)
+    est = B200Estimator(precision=precision)
+    thetas = rng.uniform(-np.pi, np.pi, (8, ansatz.num_parameters))
+    tol = 1e-12 if precision == "fp64" else 1e-5
+    for test in norm_t + over_t:
+        for circ in test.circuits:
+            got = est.run([circ] * 8, [("Z", 0)] * 8, list(thetas)).result().values
+            for k in range(8):
+                psi = numpy_sv.run(circ.num_qubits, circuit_to_stream(circ.assign_parameters(thetas[k])))
+                assert abs(got[k] - numpy_sv.expectation_z(psi, 0)) <= tol
+
+
+def test_estimator_wide_operator_matvec(cuda_device):
+    """config 3 shape: ansatz on 9 data qubits, controlled dense 9-qubit unitary, 10 qubits total."""
+    from qls_b200.circuit import QuantumCircuit
+    from qls_b200.estimator import B200Estimator
+    from qls_b200.library import RealAmplitudes
+    from qls_b200.vqls import HadamardTest
+
+    rng = np.random.default_rng(7)
+    nq = 9
+    ansatz = RealAmplitudes(nq, reps=3)
+    op = QuantumCircuit(nq)
+    op.unitary(random_unitary(nq, rng), list(range(nq)))
+    test = HadamardTest([op], apply_initial_state=ansatz)
+    thetas = rng.uniform(-np.pi, np.pi, (5, ansatz.num_parameters))
+    est = B200Estimator()
+    for circ in test.circuits:
+        got = est.run([circ] * 5, ["I" * nq + "Z"] * 5, list(thetas)).result().values
+        for k in range(5):
+            psi = numpy_sv.run(nq + 1, circuit_to_stream(circ.assign_parameters(thetas[k])))
+            assert abs(got[k] - numpy_sv.expectation_z(psi, 0)) <= 1e-12
+
+
+def test_vqls_2x2_through_the_facade(cuda_device, tmp_path, monkeypatch):
+    """Reference tests/test_vqls_implementations.py:26-37: width 1, atol 1e-3."""
+    from qls_b200.library import RealAmplitudes
+    from qls_b200.quantum_linear_solver import QuantumLinearSolver
+    from qls_b200.toymodels import Qiskit4QubitExample
+
+    monkeypatch.chdir(tmp_path)
+    model = Qiskit4QubitExample()
+    ansatz = RealAmplitudes(num_qubits=1, entanglement="full", reps=3, insert_barriers=False)
+    qls = QuantumLinearSolver()
+    x = qls.solve(model.matrix_a, model.vector_b, method="vqls_qiskit", file_basename="kat", ansatz=ansatz, seed=3)
+    assert qls.circuit_width == 1
+    assert np.allclose(model.classical_solution, x, atol=1e-3)
+    assert os.path.exists("vqls_qiskit_circuit.qasm3")
+
+
+def test_vqls_4x4_default_ansatz(cuda_device, tmp_path, monkeypatch):
+    from qls_b200.implementations.vqls_qiskit_implementation import solve_vqls_qiskit
+    from qls_b200.toymodels import ClassiqDemoExample
+
+    monkeypatch.chdir(tmp_path)
+    model = ClassiqDemoExample()
+    x, qasm, depth, width, run_time = solve_vqls_qiskit(model.matrix_a, model.vector_b, optimizer_max_iter=400, seed=1)
+    assert width == 2 and depth > 0 and qasm.startswith("OPENQASM 3")
+    rel = np.linalg.norm(model.classical_solution - x) / np.linalg.norm(model.classical_solution)
+    assert rel < 0.2  # the reference's own acceptance gate (plotting.py:136-143)
