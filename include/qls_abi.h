@@ -99,7 +99,42 @@ typedef struct QlsPass {
   int32_t n_fseg;             /* deposit of the tile counter into the free index bits         */
   QlsSeg fseg[QLS_MAX_FSEG];
   uint32_t pad;
+  uint32_t rs_begin;          /* register-stage form: records [rs_begin, rs_begin + rs_count) of   */
+  uint32_t rs_count;          /* the program's QlsRsOp array; rs_count == 0 -> sweep form only     */
 } QlsPass;
+
+/* ---- register-stage form of a pass (the fast path for full-size tiles) -----------------------
+ * The 2^tile_bits amplitudes of a tile are held in the registers of the CTA's 256 threads
+ * (2^reg_bits each).  A pass is a sequence of STAGES; a stage fixes which reg_bits tile qubits are
+ * "register qubits" (the other 8 index the thread) and applies its micro-ops entirely in
+ * registers.  Between stages the tile is exchanged through shared memory (one write + one read).
+ * Only 1- and 2-qubit dense blocks, diagonal tables and multiplexed RY are expressible; passes with
+ * wider dense blocks keep the shared-memory sweep form above. */
+enum {
+  QLS_RS_STAGE = 1, /* tseg: thread index -> tile-local index deposit; rt[r]: swizzled offset of register combo r */
+  QLS_RS_G1 = 2,    /* 2x2 on register qubit r[0]                                                  */
+  QLS_RS_G2 = 3,    /* 4x4 on register qubits r[0] < r[1] (matrix bit 0 <-> r[0])                  */
+  QLS_RS_DIAG = 4,  /* amp *= table[xseg(global base) | tseg(thread index) | rt[register combo]]    */
+  QLS_RS_MUXRY = 5  /* RY on register qubit r[0], (cos, sin) from the same kind of table index     */
+};
+
+typedef struct QlsRsOp { /* 192 bytes */
+  int32_t kind;
+  uint8_t r[4];        /* target register-qubit indexes                                           */
+  uint32_t ctl_tmask;  /* controls among the thread-index bits ...                                */
+  uint32_t ctl_tval;
+  uint32_t ctl_rmask;  /* ... and among the register-combo bits                                   */
+  uint32_t ctl_rval;
+  uint64_t xc_mask;    /* controls outside the tile (tested on the tile's global base index)      */
+  uint64_t xc_val;
+  uint64_t pool_off;
+  uint8_t n_tseg, n_xseg, flags, pad0;
+  uint32_t pad1;
+  QlsSeg tseg[QLS_MAX_SEG];
+  QlsSeg xseg[QLS_MAX_SEG];
+  uint16_t rt[32];
+  uint8_t reserved[24];
+} QlsRsOp;
 
 typedef struct QlsProgram QlsProgram; /* opaque: device copies of ops + constant pool */
 
@@ -111,7 +146,10 @@ int qls_device_info(int device, int* sm_count, uint64_t* smem_optin, uint64_t* m
 /* Upload a lowered program (passes/ops/pool are HOST arrays; pool entries are in `dtype`).
  * Synchronous.  Replaces the per-gate loop of Statevector._evolve_instruction [hhl..:49]. */
 int qls_program_create(const QlsPass* passes_host, uint32_t n_passes, const QlsOp* ops_host, uint32_t n_ops,
-                       const void* pool_host, uint64_t pool_bytes, int dtype, int device, QlsProgram** out);
+                       const QlsRsOp* rs_ops_host, uint32_t n_rs_ops, const void* pool_host, uint64_t pool_bytes,
+                       int dtype, int device, QlsProgram** out);
+/* 0: use the register-stage form where a pass has one (default); 1: always use the sweep form. */
+int qls_set_sweep_only(int on);
 int qls_program_destroy(QlsProgram* prog);
 /* Run passes [pass_begin, pass_end) on a state of 2^n_local amplitudes.  `index_offset` is the
  * global index of local amplitude 0 (rank << n_local for a sharded state, else 0). */

@@ -61,11 +61,40 @@ class QlsPass(C.Structure):
         ("n_fseg", C.c_int32),
         ("fseg", QlsSeg * QLS_MAX_FSEG),
         ("pad", C.c_uint32),
+        ("rs_begin", C.c_uint32),
+        ("rs_count", C.c_uint32),
+    ]
+
+
+QLS_RS_STAGE, QLS_RS_G1, QLS_RS_G2, QLS_RS_DIAG, QLS_RS_MUXRY = 1, 2, 3, 4, 5
+
+
+class QlsRsOp(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("r", C.c_uint8 * 4),
+        ("ctl_tmask", C.c_uint32),
+        ("ctl_tval", C.c_uint32),
+        ("ctl_rmask", C.c_uint32),
+        ("ctl_rval", C.c_uint32),
+        ("xc_mask", C.c_uint64),
+        ("xc_val", C.c_uint64),
+        ("pool_off", C.c_uint64),
+        ("n_tseg", C.c_uint8),
+        ("n_xseg", C.c_uint8),
+        ("flags", C.c_uint8),
+        ("pad0", C.c_uint8),
+        ("pad1", C.c_uint32),
+        ("tseg", QlsSeg * QLS_MAX_SEG),
+        ("xseg", QlsSeg * QLS_MAX_SEG),
+        ("rt", C.c_uint16 * 32),
+        ("reserved", C.c_uint8 * 24),
     ]
 
 
 assert C.sizeof(QlsOp) == 128, C.sizeof(QlsOp)
-assert C.sizeof(QlsPass) == 120, C.sizeof(QlsPass)
+assert C.sizeof(QlsPass) == 128, C.sizeof(QlsPass)
+assert C.sizeof(QlsRsOp) == 192, C.sizeof(QlsRsOp)
 
 # every symbol declared in include/qls_abi.h: name -> (restype, argtypes)
 _vp, _u64, _u32, _i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
@@ -73,7 +102,9 @@ SYMBOLS = {
     "qls_abi_version": (_i, []),
     "qls_last_error": (C.c_char_p, []),
     "qls_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
-    "qls_program_create": (_i, [C.POINTER(QlsPass), _u32, C.POINTER(QlsOp), _u32, _vp, _u64, _i, _i, C.POINTER(_vp)]),
+    "qls_program_create": (_i, [C.POINTER(QlsPass), _u32, C.POINTER(QlsOp), _u32, C.POINTER(QlsRsOp), _u32, _vp, _u64, _i, _i,
+                                C.POINTER(_vp)]),
+    "qls_set_sweep_only": (_i, [_i]),
     "qls_program_destroy": (_i, [_vp]),
     "qls_program_run": (_i, [_vp, _vp, _i, _u64, _u32, _u32, _vp]),
     "qls_sv_init_basis": (_i, [_vp, _i, _i, _u64, _vp]),

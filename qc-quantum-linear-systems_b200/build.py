@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libqls_b200.so")
-SOURCES = ["state_ops.cu", "tile_pass.cu", "ctrl_gemm.cu", "batch_sv.cu", "remap.cu"]
+SOURCES = ["state_ops.cu", "tile_pass.cu", "rs_pass.cu", "ctrl_gemm.cu", "batch_sv.cu", "remap.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,

@@ -7,7 +7,8 @@
 #include "qls_abi.h"
 
 static_assert(sizeof(QlsOp) == 128, "QlsOp must be 128 bytes (mirrored in _abi.py)");
-static_assert(sizeof(QlsPass) == 120, "QlsPass must be 120 bytes (mirrored in _abi.py)");
+static_assert(sizeof(QlsPass) == 128, "QlsPass must be 128 bytes (mirrored in _abi.py)");
+static_assert(sizeof(QlsRsOp) == 192, "QlsRsOp must be 192 bytes (mirrored in _abi.py)");
 
 void qls_set_error(const char* fmt, ...);
 
@@ -34,9 +35,16 @@ struct QlsProgram {
   uint32_t n_passes, n_ops;
   QlsPass* passes_host;  // host copy (launch geometry is computed on the host)
   QlsOp* ops_dev;
+  QlsRsOp* rs_ops_dev;
+  uint32_t n_rs_ops;
   unsigned char* pool_dev;
   uint64_t pool_bytes;
 };
+
+// register-stage fast path (rs_pass.cu)
+bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, int n_local);
+int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset,
+                       cudaStream_t stream);
 
 // ---- complex arithmetic on double2 / float2 -----------------------------------------------------
 template <typename R>

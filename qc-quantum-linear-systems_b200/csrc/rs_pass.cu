@@ -1,0 +1,345 @@
+// Register-stage tile-pass kernel (the fast path for full-size tiles).
+//
+// Persistent CTAs (2 per SM, 256 threads).  A tile of 2^T amplitudes (T = 12 complex128 /
+// 13 complex64 -> 64 KB) is staged into shared memory with 16-byte cp.async, then lives in the
+// registers of the CTA: every thread holds 2^KR amplitudes (KR = 4 / 5: the stage's "register
+// qubits"), the remaining 8 tile bits are the thread index.  All micro-ops of a stage -- 1- and
+// 2-qubit dense blocks on register qubits, diagonal tables, multiplexed RY -- run on registers with
+// compile-time register indices; shared memory is touched only to load, to re-distribute the tile
+// between stages (one write + one read), and to write back.  The shared-memory image is XOR
+// swizzled so that both the coalesced global<->shared copies and the strided per-stage accesses
+// spread over the banks.  Address arithmetic that does not depend on the tile (thread -> index
+// deposits, high-qubit spreads, op records) is computed once per CTA, not once per amplitude.
+#include "qls_common.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_MAX_OPS = 128;
+constexpr int RS_MAX_STAGES = 24;
+
+struct RsLaunch {
+  int L, n_high, n_fseg, n_rs;
+  uint8_t high[QLS_MAX_HIGH];
+  QlsSeg fseg[QLS_MAX_FSEG];
+  uint64_t fix_val;
+  uint64_t index_offset;
+  uint64_t n_tiles;
+};
+
+// swizzle of a tile-local amplitude index; SH = log2(amplitudes per 16-byte unit)
+template <int SH>
+__device__ __forceinline__ uint32_t swz(uint32_t i) {
+  const uint32_t u = i >> SH;
+  return i ^ ((((u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7u) << SH);
+}
+
+template <typename V, int A, int RQ, bool REAL>
+__device__ __forceinline__ void rs_g1(V (&a)[A], const V* __restrict__ M, bool tok, uint32_t rmask, uint32_t rval) {
+  const V m00 = __ldg(M), m01 = __ldg(M + 1), m10 = __ldg(M + 2), m11 = __ldg(M + 3);
+#pragma unroll
+  for (int p = 0; p < A / 2; ++p) {
+    const int i0 = ((p >> RQ) << (RQ + 1)) | (p & ((1 << RQ) - 1));
+    const int i1 = i0 | (1 << RQ);
+    if (tok && (((uint32_t)i0 & rmask) == rval)) {
+      const V x = a[i0], y = a[i1];
+      V b0, b1;
+      if (REAL) {
+        b0.x = fma(m01.x, y.x, m00.x * x.x);
+        b0.y = fma(m01.x, y.y, m00.x * x.y);
+        b1.x = fma(m11.x, y.x, m10.x * x.x);
+        b1.y = fma(m11.x, y.y, m10.x * x.y);
+      } else {
+        b0 = cmul(m00, x);
+        cfma(b0, m01, y);
+        b1 = cmul(m10, x);
+        cfma(b1, m11, y);
+      }
+      a[i0] = b0;
+      a[i1] = b1;
+    }
+  }
+}
+
+template <typename V, int A, int R1, int R2>
+__device__ __forceinline__ void rs_g2(V (&a)[A], const V* __restrict__ M, bool tok, uint32_t rmask, uint32_t rval) {
+  static_assert(R1 < R2, "register qubits must be ascending");
+#pragma unroll
+  for (int g = 0; g < A / 4; ++g) {
+    const int t0 = ((g >> R1) << (R1 + 1)) | (g & ((1 << R1) - 1));               // zero at R1
+    const int i00 = ((t0 >> R2) << (R2 + 1)) | (t0 & ((1 << R2) - 1));            // zero at R2
+    const int i01 = i00 | (1 << R1), i10 = i00 | (1 << R2), i11 = i01 | (1 << R2);
+    if (tok && (((uint32_t)i00 & rmask) == rval)) {
+      const V x0 = a[i00], x1 = a[i01], x2 = a[i10], x3 = a[i11];
+      V o[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        o[r] = cmul(__ldg(M + 4 * r), x0);
+        cfma(o[r], __ldg(M + 4 * r + 1), x1);
+        cfma(o[r], __ldg(M + 4 * r + 2), x2);
+        cfma(o[r], __ldg(M + 4 * r + 3), x3);
+      }
+      a[i00] = o[0];
+      a[i01] = o[1];
+      a[i10] = o[2];
+      a[i11] = o[3];
+    }
+  }
+}
+
+template <typename V, int A>
+__device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
+#pragma unroll
+  for (int r = 0; r < A; ++r) {
+    if (tok && (((uint32_t)r & op.ctl_rmask) == op.ctl_rval)) a[r] = cmul(a[r], __ldg(&table[ti0 | op.rt[r]]));
+  }
+}
+
+template <typename V, int A, int RQ>
+__device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
+#pragma unroll
+  for (int p = 0; p < A / 2; ++p) {
+    const int i0 = ((p >> RQ) << (RQ + 1)) | (p & ((1 << RQ) - 1));
+    const int i1 = i0 | (1 << RQ);
+    if (tok && (((uint32_t)i0 & op.ctl_rmask) == op.ctl_rval)) {
+      const V cs = __ldg(&table[ti0 | op.rt[i0]]);
+      const V x = a[i0], y = a[i1];
+      V b0, b1;
+      b0.x = cs.x * x.x - cs.y * y.x;
+      b0.y = cs.x * x.y - cs.y * y.y;
+      b1.x = cs.y * x.x + cs.x * y.x;
+      b1.y = cs.y * x.y + cs.x * y.y;
+      a[i0] = b0;
+      a[i1] = b1;
+    }
+  }
+}
+
+template <typename V, int A, int KR>
+__device__ __forceinline__ void rs_dispatch_g1(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
+  const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
+  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
+#define QLS_G1_CASE(q)                                       \
+  case q:                                                    \
+    if (real) rs_g1<V, A, q, true>(a, M, tok, rm, rv);       \
+    else rs_g1<V, A, q, false>(a, M, tok, rm, rv);           \
+    break;
+  switch (op.r[0]) {
+    QLS_G1_CASE(0)
+    QLS_G1_CASE(1)
+    QLS_G1_CASE(2)
+    QLS_G1_CASE(3)
+    case 4:
+      if constexpr (KR >= 5) {
+        if (real) rs_g1<V, A, 4, true>(a, M, tok, rm, rv);
+        else rs_g1<V, A, 4, false>(a, M, tok, rm, rv);
+      }
+      break;
+  }
+#undef QLS_G1_CASE
+}
+
+template <typename V, int A, int KR>
+__device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
+  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
+#define QLS_G2_CASE(p, q) \
+  case (p * 8 + q):       \
+    rs_g2<V, A, p, q>(a, M, tok, rm, rv); \
+    break;
+  switch (op.r[0] * 8 + op.r[1]) {
+    QLS_G2_CASE(0, 1)
+    QLS_G2_CASE(0, 2)
+    QLS_G2_CASE(0, 3)
+    QLS_G2_CASE(1, 2)
+    QLS_G2_CASE(1, 3)
+    QLS_G2_CASE(2, 3)
+    default:
+      if constexpr (KR >= 5) {
+        switch (op.r[0]) {
+          case 0: rs_g2<V, A, 0, 4>(a, M, tok, rm, rv); break;
+          case 1: rs_g2<V, A, 1, 4>(a, M, tok, rm, rv); break;
+          case 2: rs_g2<V, A, 2, 4>(a, M, tok, rm, rv); break;
+          case 3: rs_g2<V, A, 3, 4>(a, M, tok, rm, rv); break;
+        }
+      }
+      break;
+  }
+#undef QLS_G2_CASE
+}
+
+template <typename V, int A, int KR>
+__device__ __forceinline__ void rs_dispatch_muxry(V (&a)[A], const QlsRsOp& op, const V* table, uint32_t ti0, bool tok) {
+  switch (op.r[0]) {
+    case 0: rs_muxry<V, A, 0>(a, op, table, ti0, tok); break;
+    case 1: rs_muxry<V, A, 1>(a, op, table, ti0, tok); break;
+    case 2: rs_muxry<V, A, 2>(a, op, table, ti0, tok); break;
+    case 3: rs_muxry<V, A, 3>(a, op, table, ti0, tok); break;
+    case 4:
+      if constexpr (KR >= 5) rs_muxry<V, A, 4>(a, op, table, ti0, tok);
+      break;
+  }
+}
+
+template <typename R, int T, int KR>
+__global__ void __launch_bounds__(RS_THREADS, 2)
+    qls_rs_pass_kernel(typename Vec2<R>::type* __restrict__ state, const RsLaunch rl, const QlsRsOp* __restrict__ rs_ops,
+                       const unsigned char* __restrict__ pool) {
+  using V = typename Vec2<R>::type;
+  static_assert(T - KR == 8, "256 threads index the non-register tile bits");
+  constexpr int A = 1 << KR;
+  constexpr int SH = sizeof(V) == 16 ? 0 : 1;
+  constexpr int APU = 1 << SH;           // amplitudes per 16-byte unit
+  constexpr int UNITS = (1 << T) / APU;  // 4096
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* sm = reinterpret_cast<V*>(smem_raw);
+  uint4* sm16 = reinterpret_cast<uint4*>(smem_raw);
+  QlsRsOp* sops = reinterpret_cast<QlsRsOp*>(smem_raw + (sizeof(V) << T));
+  uint64_t* hoff = reinterpret_cast<uint64_t*>(sops + rl.n_rs);            // [1 << n_high]
+  uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << rl.n_high));    // [stages][256]
+
+  const int tid = threadIdx.x;
+  const int L = rl.L;
+
+  // ---- once per CTA ----------------------------------------------------------------------------
+  for (int i = tid; i < rl.n_rs * (int)(sizeof(QlsRsOp) / 16); i += RS_THREADS)
+    reinterpret_cast<uint4*>(sops)[i] = reinterpret_cast<const uint4*>(rs_ops)[i];
+  for (int r = tid; r < (1 << rl.n_high); r += RS_THREADS) {
+    uint64_t g = 0;
+    for (int j = 0; j < rl.n_high; ++j) g |= (uint64_t)((r >> j) & 1) << rl.high[j];
+    hoff[r] = g;
+  }
+  __syncthreads();
+  {
+    int st = 0;
+    for (int o = 0; o < rl.n_rs; ++o) {
+      if (sops[o].kind == QLS_RS_STAGE) {
+        const uint32_t tb = gather_segs32((uint32_t)tid, sops[o].tseg, sops[o].n_tseg);
+        ptb[st * RS_THREADS + tid] = (uint16_t)swz<SH>(tb);
+        ++st;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- persistent loop over tiles ------------------------------------------------------------------
+  for (uint64_t tile = blockIdx.x; tile < rl.n_tiles; tile += gridDim.x) {
+    const uint64_t base = gather_segs64(tile, rl.fseg, rl.n_fseg) | rl.fix_val;
+    const uint64_t gbase = base | rl.index_offset;
+
+#pragma unroll 4
+    for (int u = tid; u < UNITS; u += RS_THREADS) {
+      const int i = u * APU;
+      const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
+      cp_async16(&sm16[swz<SH>((uint32_t)i) >> SH], &state[g]);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    V a[A];
+    int stage = -1;
+    uint32_t mytb = 0;
+    const QlsRsOp* cur = nullptr;
+    for (int o = 0; o < rl.n_rs; ++o) {
+      const QlsRsOp& op = sops[o];
+      if (op.kind == QLS_RS_STAGE) {
+        if (stage >= 0) {
+#pragma unroll
+          for (int r = 0; r < A; ++r) sm[mytb ^ cur->rt[r]] = a[r];
+          __syncthreads();
+        }
+        ++stage;
+        cur = &op;
+        mytb = ptb[stage * RS_THREADS + tid];
+#pragma unroll
+        for (int r = 0; r < A; ++r) a[r] = sm[mytb ^ op.rt[r]];
+        __syncthreads();
+        continue;
+      }
+      if ((gbase & op.xc_mask) != op.xc_val) continue;  // block-uniform
+      const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;
+      const V* data = reinterpret_cast<const V*>(pool + op.pool_off);
+      switch (op.kind) {
+        case QLS_RS_G1:
+          rs_dispatch_g1<V, A, KR>(a, op, data, tok);
+          break;
+        case QLS_RS_G2:
+          rs_dispatch_g2<V, A, KR>(a, op, data, tok);
+          break;
+        case QLS_RS_DIAG: {
+          const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
+          rs_diag<V, A>(a, op, data, ti0, tok);
+          break;
+        }
+        case QLS_RS_MUXRY: {
+          const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
+          rs_dispatch_muxry<V, A, KR>(a, op, data, ti0, tok);
+          break;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < A; ++r) sm[mytb ^ cur->rt[r]] = a[r];
+    __syncthreads();
+
+#pragma unroll 4
+    for (int u = tid; u < UNITS; u += RS_THREADS) {
+      const int i = u * APU;
+      const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
+      *reinterpret_cast<uint4*>(&state[g]) = sm16[swz<SH>((uint32_t)i) >> SH];
+    }
+    __syncthreads();  // the next tile's cp.async must not overtake these reads
+  }
+}
+
+template <typename R, int T, int KR>
+int launch_rs(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset, cudaStream_t stream) {
+  using V = typename Vec2<R>::type;
+  RsLaunch rl;
+  memset(&rl, 0, sizeof(rl));
+  rl.L = p.low_bits;
+  rl.n_high = p.n_high;
+  rl.n_fseg = p.n_fseg;
+  rl.n_rs = (int)p.rs_count;
+  memcpy(rl.high, p.high, sizeof(rl.high));
+  memcpy(rl.fseg, p.fseg, sizeof(rl.fseg));
+  rl.fix_val = p.fix_val;
+  rl.index_offset = index_offset;
+  const int fixed = __builtin_popcountll(p.fix_mask);
+  const int free_bits = n_local - p.tile_bits - fixed;
+  QLS_ARG(free_bits >= 0 && free_bits < 40, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
+  rl.n_tiles = 1ull << free_bits;
+  int n_stages = p.pad >> 8;  // counted by qls_program_create
+  const size_t smem = ((size_t)sizeof(V) << T) + (size_t)p.rs_count * sizeof(QlsRsOp) + (sizeof(uint64_t) << p.n_high) +
+                      (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
+  QLS_ARG(smem <= 112 * 1024, "register-stage pass needs %zu bytes of shared memory", smem);
+  auto kern = qls_rs_pass_kernel<R, T, KR>;
+  static bool attr_set[64] = {false};
+  static int sm_count[64] = {0};
+  if (!attr_set[prog->device & 63]) {
+    QLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    QLS_CUDA(cudaDeviceGetAttribute(&sm_count[prog->device & 63], cudaDevAttrMultiProcessorCount, prog->device));
+    attr_set[prog->device & 63] = true;
+  }
+  uint64_t grid = 2ull * (uint64_t)sm_count[prog->device & 63];
+  if (grid > rl.n_tiles) grid = rl.n_tiles;
+  kern<<<(unsigned)grid, RS_THREADS, smem, stream>>>(reinterpret_cast<V*>(state), rl, prog->rs_ops_dev + p.rs_begin,
+                                                     prog->pool_dev);
+  QLS_CUDA(cudaGetLastError());
+  return QLS_OK;
+}
+
+}  // namespace
+
+// true if pass `p` of `prog` can run in register-stage form on a state of n_local qubits
+bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, int n_local) {
+  const int want_T = prog->dtype == QLS_C128 ? 12 : 13;
+  return p.rs_count > 0 && p.rs_count <= (uint32_t)RS_MAX_OPS && p.tile_bits == want_T && n_local >= want_T &&
+         (int)(p.pad >> 8) >= 1 && (int)(p.pad >> 8) <= RS_MAX_STAGES;
+}
+
+int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset,
+                       cudaStream_t stream) {
+  if (prog->dtype == QLS_C128) return launch_rs<double, 12, 4>(prog, p, state, n_local, index_offset, stream);
+  return launch_rs<float, 13, 5>(prog, p, state, n_local, index_offset, stream);
+}

@@ -108,6 +108,12 @@ static int validate_pass(const QlsPass& p, int n_local, int dtype) {
   return QLS_OK;
 }
 
+static int g_sweep_only = 0;
+extern "C" int qls_set_sweep_only(int on) {
+  g_sweep_only = on ? 1 : 0;
+  return QLS_OK;
+}
+
 extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset,
                                uint32_t pass_begin, uint32_t pass_end, void* stream) {
   QLS_ARG(prog && state, "null program or state");
@@ -120,6 +126,11 @@ extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local,
     int rc = validate_pass(p, n_local, prog->dtype);
     if (rc) return rc;
     QLS_ARG(!(p.pad & 4u), "pass %u holds batch-only ops (PARAM / MATVEC): use qls_batch_expect_z", i);
+    if (!g_sweep_only && qls_rs_eligible(prog, p, n_local)) {
+      rc = qls_launch_rs_pass(prog, p, state, n_local, index_offset, s);
+      if (rc) return rc;
+      continue;
+    }
     bool heavy = (p.pad & 1u) != 0;  // set by qls_program_create when the pass holds a k >= 4 dense op
     if (prog->dtype == QLS_C128)
       rc = heavy ? launch_pass<double, true>(prog, p, state, n_local, index_offset, s)
@@ -133,11 +144,13 @@ extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local,
 }
 
 extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes, const QlsOp* ops_host, uint32_t n_ops,
-                                  const void* pool_host, uint64_t pool_bytes, int dtype, int device, QlsProgram** out) {
+                                  const QlsRsOp* rs_ops_host, uint32_t n_rs_ops, const void* pool_host,
+                                  uint64_t pool_bytes, int dtype, int device, QlsProgram** out) {
   QLS_ARG(out, "null out");
   QLS_ARG(dtype == QLS_C128 || dtype == QLS_C64, "bad dtype %d", dtype);
   QLS_ARG(n_passes == 0 || passes_host, "null passes");
   QLS_ARG(n_ops == 0 || ops_host, "null ops");
+  QLS_ARG(n_rs_ops == 0 || rs_ops_host, "null register-stage ops");
   QLS_CUDA(cudaSetDevice(device));
   const size_t esz = dtype == QLS_C128 ? 16 : 8;
   for (uint32_t i = 0; i < n_ops; ++i) {
@@ -156,8 +169,18 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
       for (int j = 1; j < op.k; ++j) QLS_ARG(op.tq[j] > op.tq[j - 1], "op %u: targets not ascending", i);
     }
   }
+  for (uint32_t i = 0; i < n_rs_ops; ++i) {
+    const QlsRsOp& op = rs_ops_host[i];
+    QLS_ARG(op.kind >= QLS_RS_STAGE && op.kind <= QLS_RS_MUXRY, "rs op %u: bad kind %d", i, op.kind);
+    QLS_ARG(op.n_tseg <= QLS_MAX_SEG && op.n_xseg <= QLS_MAX_SEG, "rs op %u: too many segments", i);
+    if (op.kind != QLS_RS_STAGE) QLS_ARG(op.pool_off % esz == 0 && op.pool_off < pool_bytes, "rs op %u: bad pool offset", i);
+    if (op.kind == QLS_RS_G2) QLS_ARG(op.r[0] < op.r[1] && op.r[1] < 5, "rs op %u: bad register qubits", i);
+    if (op.kind == QLS_RS_G1 || op.kind == QLS_RS_MUXRY) QLS_ARG(op.r[0] < 5, "rs op %u: bad register qubit", i);
+  }
   QlsProgram* p = new QlsProgram();
   p->device = device;
+  p->rs_ops_dev = nullptr;
+  p->n_rs_ops = n_rs_ops;
   p->dtype = dtype;
   p->n_passes = n_passes;
   p->n_ops = n_ops;
@@ -188,12 +211,27 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
           return QLS_ERR_ARG;
         }
     }
-    ps.pad = (heavy ? 1u : 0u) | (matvec ? 2u : 0u) | (batch_only ? 4u : 0u);
+    uint32_t n_stages = 0;
+    if ((uint64_t)ps.rs_begin + ps.rs_count > n_rs_ops) {
+      qls_set_error("pass %u: register-stage range outside program", i);
+      delete[] p->passes_host;
+      delete p;
+      return QLS_ERR_ARG;
+    }
+    for (uint32_t o = ps.rs_begin; o < ps.rs_begin + ps.rs_count; ++o)
+      if (rs_ops_host[o].kind == QLS_RS_STAGE) ++n_stages;
+    if (ps.rs_count && rs_ops_host[ps.rs_begin].kind != QLS_RS_STAGE) n_stages = 0;  // malformed: disables the form
+    ps.pad = (heavy ? 1u : 0u) | (matvec ? 2u : 0u) | (batch_only ? 4u : 0u) | (n_stages << 8);
   }
   cudaError_t e = cudaSuccess;
   if (n_ops) {
     e = cudaMalloc(&p->ops_dev, sizeof(QlsOp) * (size_t)n_ops);
     if (e == cudaSuccess) e = cudaMemcpy(p->ops_dev, ops_host, sizeof(QlsOp) * (size_t)n_ops, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && n_rs_ops) {
+    e = cudaMalloc(&p->rs_ops_dev, sizeof(QlsRsOp) * (size_t)n_rs_ops);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->rs_ops_dev, rs_ops_host, sizeof(QlsRsOp) * (size_t)n_rs_ops, cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess && pool_bytes) {
     e = cudaMalloc(&p->pool_dev, pool_bytes);
@@ -202,6 +240,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   if (e != cudaSuccess) {
     qls_set_error("qls_program_create: %s", cudaGetErrorString(e));
     if (p->ops_dev) cudaFree(p->ops_dev);
+    if (p->rs_ops_dev) cudaFree(p->rs_ops_dev);
     if (p->pool_dev) cudaFree(p->pool_dev);
     delete[] p->passes_host;
     delete p;
@@ -215,6 +254,7 @@ extern "C" int qls_program_destroy(QlsProgram* prog) {
   if (!prog) return QLS_OK;
   cudaSetDevice(prog->device);
   if (prog->ops_dev) cudaFree(prog->ops_dev);
+  if (prog->rs_ops_dev) cudaFree(prog->rs_ops_dev);
   if (prog->pool_dev) cudaFree(prog->pool_dev);
   delete[] prog->passes_host;
   delete prog;

@@ -129,7 +129,8 @@ class DeviceProgram:
         pool = lowered.pool
         with torch.cuda.device(self.device):
             _abi.check(self.lib.qls_program_create(lowered.passes, lowered.n_passes, lowered.ops,
-                                                   sum(p.n_ops for p in lowered.pass_info), pool.ctypes.data, pool.size,
+                                                   sum(p.n_ops for p in lowered.pass_info), lowered.rs_ops,
+                                                   lowered.n_rs_ops, pool.ctypes.data, pool.size,
                                                    self.abi_dtype, self.device, C.byref(handle)))
         self.handle = handle
         self._gemm_mats = {}

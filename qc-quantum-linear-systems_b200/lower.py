@@ -352,10 +352,11 @@ class LoweringOptions:
     dtype: str = "fp64"  # "fp64" (complex128) | "fp32" (complex64)
     tile_bits: int = 0  # 0 -> 12 (fp64) / 13 (fp32)
     max_high: int = 5  # tile qubits above the contiguous low run
-    max_fuse_qubits: int = 3
+    max_fuse_qubits: int = 2  # 2 keeps every block expressible as register-stage micro-ops
     max_diag_qubits: int = 10
     n_local: int = 0  # 0 -> all qubits local (single GPU)
     batch: bool = False  # one whole-state pass for qls_batch_expect_z (parameterised, n <= 12/13)
+    register_stages: bool = True  # also emit the register-stage form of passes that can use it
 
     def resolved_tile_bits(self) -> int:
         return self.tile_bits or (12 if self.dtype == "fp64" else 13)
@@ -385,6 +386,7 @@ class PassInfo:
     n_source: int
     op_controls: List[int]
     heavy: bool
+    rs_stages: int = 0  # > 0: the pass also has a register-stage form with this many stages
 
 
 @dataclass
@@ -395,6 +397,8 @@ class LoweredProgram:
     steps: List[Step]
     passes: "C.Array"
     ops: "C.Array"
+    rs_ops: "C.Array"
+    n_rs_ops: int
     pool: np.ndarray
     pass_info: List[PassInfo]
     n_source_gates: int
@@ -439,6 +443,10 @@ def _segments(pairs: List[Tuple[int, int]]) -> List[Tuple[int, int, int]]:
     return [tuple(s) for s in segs]
 
 
+class _RsUnsupported(Exception):
+    pass
+
+
 class _Emitter:
     def __init__(self, n: int, opts: LoweringOptions):
         self.n = n
@@ -453,6 +461,9 @@ class _Emitter:
         self.cdtype = np.complex128 if opts.dtype == "fp64" else np.complex64
         self.passes: List[_abi.QlsPass] = []
         self.ops: List[_abi.QlsOp] = []
+        self.rs_ops: List[_abi.QlsRsOp] = []
+        self.rs_T = 12 if opts.dtype == "fp64" else 13
+        self.rs_KR = self.rs_T - 8
         self.pool = bytearray()
         self.pass_info: List[PassInfo] = []
         self.steps: List[Step] = []
@@ -591,7 +602,12 @@ class _Emitter:
             heavy |= b.kind == "dense" and len(b.targets) >= 4
         flush_pending()
 
+        rs_begin = len(self.rs_ops)
+        rs_stages = 0
+        if self.opts.register_stages and not self.opts.batch and T == self.rs_T:
+            rs_stages = self._emit_register_stages(blocks, local_pos, common)
         p = _abi.QlsPass()
+        p.rs_begin, p.rs_count = rs_begin, len(self.rs_ops) - rs_begin
         p.tile_bits, p.low_bits, p.n_high = T, L, len(high_sorted)
         for j, q in enumerate(high_sorted):
             p.high[j] = q
@@ -606,11 +622,182 @@ class _Emitter:
             p.fseg[j].src, p.fseg[j].width, p.fseg[j].dst = src, w, dst
         idx = len(self.passes)
         self.passes.append(p)
-        self.pass_info.append(PassInfo(T, L, high_sorted, len(common), p.op_count, n_source, op_controls, heavy))
+        self.pass_info.append(PassInfo(T, L, high_sorted, len(common), p.op_count, n_source, op_controls, heavy, rs_stages))
         if self.steps and self.steps[-1].kind == "passes" and self.steps[-1].pass_end == idx:
             self.steps[-1].pass_end = idx + 1
         else:
             self.steps.append(Step("passes", pass_begin=idx, pass_end=idx + 1))
+
+    # -- register-stage form --------------------------------------------------------------
+    def _swz(self, i: int) -> int:
+        sh = 0 if self.opts.dtype == "fp64" else 1
+        u = i >> sh
+        return i ^ ((((u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7) << sh)
+
+    def _emit_register_stages(self, blocks: Sequence[Block], local_pos: Dict[int, int], common: Dict[int, int]) -> int:
+        """Emit the pass as stages of register-resident micro-ops (csrc/rs_pass.cu).  Returns the
+        number of stages, or 0 (and emits nothing) if some block cannot be expressed."""
+        T, KR = self.rs_T, self.rs_KR
+        for b in blocks:
+            if b.kind == "dense" and len(b.targets) > 2:
+                return 0
+            if b.kind not in ("dense", "diag", "muxry"):
+                return 0
+        # greedy stage partition: a block joins the stage if its targets still fit the register qubits
+        stages: List[Tuple[set, List[Block]]] = []
+        cur_r: set = set()
+        cur_b: List[Block] = []
+        for b in blocks:
+            need = {local_pos[q] for q in b.touched}
+            if len(cur_r | need) > KR:
+                stages.append((cur_r, cur_b))
+                cur_r, cur_b = set(), []
+            cur_r |= need
+            cur_b.append(b)
+        stages.append((cur_r, cur_b))
+        if len(stages) > 24:
+            return 0
+        mark = len(self.rs_ops)
+        n_records = 0
+        try:
+            for rset, sblocks in stages:
+                regq = set(rset)
+                pos = T - 1
+                while len(regq) < KR:  # pad with the highest unused tile positions (lanes keep the low bits)
+                    if pos not in regq:
+                        regq.add(pos)
+                    pos -= 1
+                regq_sorted = sorted(regq)
+                rho = {p_: j for j, p_ in enumerate(regq_sorted)}
+                tpos = [p_ for p_ in range(T) if p_ not in regq]
+                tbit = {p_: j for j, p_ in enumerate(tpos)}
+                st = _abi.QlsRsOp()
+                st.kind = _abi.QLS_RS_STAGE
+                for j, p_ in enumerate(regq_sorted[:4]):
+                    st.r[j] = p_
+                segs = _segments([(j, p_) for j, p_ in enumerate(tpos)])
+                if len(segs) > _abi.QLS_MAX_SEG:
+                    raise _RsUnsupported("thread deposit needs too many segments")
+                st.n_tseg = len(segs)
+                for j, (src, w, dst) in enumerate(segs):
+                    st.tseg[j].src, st.tseg[j].width, st.tseg[j].dst = src, w, dst
+                for r in range(2**KR):
+                    off = sum(((r >> j) & 1) << regq_sorted[j] for j in range(KR))
+                    st.rt[r] = self._swz(off)
+                self.rs_ops.append(st)
+                for b in sblocks:
+                    for op in self._emit_rs_block(b, local_pos, rho, tbit, common):
+                        self.rs_ops.append(op)
+                n_records = len(self.rs_ops) - mark
+                if n_records > 128:
+                    raise _RsUnsupported("too many micro-ops")
+        except _RsUnsupported:
+            del self.rs_ops[mark:]
+            return 0
+        return len(stages)
+
+    def _rs_controls(self, op: _abi.QlsRsOp, controls: Dict[int, int], local_pos, rho, tbit) -> None:
+        for q, v in controls.items():
+            lp = local_pos.get(q)
+            if lp is None:
+                op.xc_mask |= 1 << q
+                op.xc_val |= v << q
+            elif lp in rho:
+                op.ctl_rmask |= 1 << rho[lp]
+                op.ctl_rval |= v << rho[lp]
+            else:
+                op.ctl_tmask |= 1 << tbit[lp]
+                op.ctl_tval |= v << tbit[lp]
+
+    def _rs_table_fields(self, op: _abi.QlsRsOp, qubits: Sequence[int], local_pos, rho, tbit) -> bool:
+        """Index fields of a table whose bit j is ``qubits[j]``: thread bits -> tseg, register
+        qubits -> rt[], everything else -> xseg on the global base index."""
+        if len(qubits) > 16:
+            return False
+        tpairs, xpairs, rbits = [], [], []
+        for j, q in enumerate(qubits):
+            lp = local_pos.get(q)
+            if lp is None:
+                xpairs.append((q, j))
+            elif lp in rho:
+                rbits.append((rho[lp], j))
+            else:
+                tpairs.append((tbit[lp], j))
+        tpairs.sort()
+        ts, xs = _segments(tpairs), _segments(xpairs)
+        if len(ts) > _abi.QLS_MAX_SEG or len(xs) > _abi.QLS_MAX_SEG:
+            return False
+        op.n_tseg, op.n_xseg = len(ts), len(xs)
+        for j, (src, w, dst) in enumerate(ts):
+            op.tseg[j].src, op.tseg[j].width, op.tseg[j].dst = src, w, dst
+        for j, (src, w, dst) in enumerate(xs):
+            op.xseg[j].src, op.xseg[j].width, op.xseg[j].dst = src, w, dst
+        for r in range(2**self.rs_KR):
+            op.rt[r] = sum(((r >> rb) & 1) << j for rb, j in rbits)
+        return True
+
+    def _emit_rs_block(self, b: Block, local_pos, rho, tbit, common):
+        if b.kind == "dense":
+            op = _abi.QlsRsOp()
+            regs = [rho[local_pos[q]] for q in b.targets]
+            m = b.matrix
+            if len(regs) == 1:
+                op.kind = _abi.QLS_RS_G1
+                op.r[0] = regs[0]
+                if not np.any(m.imag):
+                    op.flags |= _abi.QLS_OP_FLAG_REAL
+            else:
+                op.kind = _abi.QLS_RS_G2
+                if regs[0] > regs[1]:
+                    m = _permute_matrix(m, [1, 0])
+                    regs = [regs[1], regs[0]]
+                op.r[0], op.r[1] = regs
+            op.pool_off = self._pool_add(m)
+            self._rs_controls(op, b.controls, local_pos, rho, tbit)
+            yield op
+        elif b.kind == "muxry":
+            op = _abi.QlsRsOp()
+            op.kind = _abi.QLS_RS_MUXRY
+            op.r[0] = rho[local_pos[b.targets[0]]]
+            sel = sorted(b.selectors)
+            ang = _mux_expand(b.angles, b.selectors, sel) if list(sel) != list(b.selectors) else b.angles
+            if not self._rs_table_fields(op, sel, local_pos, rho, tbit):
+                raise _RsUnsupported("multiplexer table fields")
+            op.pool_off = self._pool_add(np.cos(ang / 2) + 1j * np.sin(ang / 2))
+            yield op
+        elif b.kind == "diag":
+            bb = b if all(q in common for q in b.controls) else _fold_diag_block(b)
+            cur: List[Tuple[Tuple[int, ...], np.ndarray]] = []
+            groups: List[List[Tuple[Tuple[int, ...], np.ndarray]]] = []
+            for f in bb.factors:
+                trial = cur + [f]
+                qs = sorted({q for fq, _ in trial for q in fq})
+                if len(qs) <= self.opts.max_diag_qubits and self._rs_table_fields(_abi.QlsRsOp(), qs, local_pos, rho, tbit):
+                    cur = trial
+                else:
+                    if not cur:
+                        raise _RsUnsupported("diagonal table fields")
+                    groups.append(cur)
+                    cur = [f]
+            if cur:
+                groups.append(cur)
+            for g in groups:
+                qs = sorted({q for fq, _ in g for q in fq})
+                tab = np.ones(2 ** len(qs), dtype=complex)
+                pos = {q: j for j, q in enumerate(qs)}
+                idx = np.arange(tab.size)
+                for fq, ft in g:
+                    sub = np.zeros_like(idx)
+                    for j, q in enumerate(fq):
+                        sub |= ((idx >> pos[q]) & 1) << j
+                    tab *= ft[sub]
+                op = _abi.QlsRsOp()
+                op.kind = _abi.QLS_RS_DIAG
+                self._rs_table_fields(op, qs, local_pos, rho, tbit)
+                op.pool_off = self._pool_add(tab)
+                yield op
+        else:
+            raise _RsUnsupported(b.kind)
 
     # -- op emission ----------------------------------------------------------------------
     def _controls(self, op: _abi.QlsOp, controls: Dict[int, int], local_pos: Dict[int, int]) -> None:
@@ -731,9 +918,10 @@ def lower_blocks(num_qubits: int, blocks: Sequence[Block], opts: LoweringOptions
     em.flush()
     passes = (_abi.QlsPass * max(1, len(em.passes)))(*em.passes)
     ops = (_abi.QlsOp * max(1, len(em.ops)))(*em.ops)
+    rs_ops = (_abi.QlsRsOp * max(1, len(em.rs_ops)))(*em.rs_ops)
     pool = np.frombuffer(bytes(em.pool) if em.pool else b"\0" * 16, dtype=np.uint8).copy()
-    return LoweredProgram(num_qubits, em.n_local, opts.dtype, em.steps, passes, ops, pool, em.pass_info,
-                          n_source_gates, global_phase)
+    return LoweredProgram(num_qubits, em.n_local, opts.dtype, em.steps, passes, ops, rs_ops, len(em.rs_ops), pool,
+                          em.pass_info, n_source_gates, global_phase)
 
 
 def lower_leaves(num_qubits: int, leaves: Sequence[Leaf], global_phase: float = 0.0,

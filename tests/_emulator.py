@@ -23,6 +23,97 @@ def _insert_zero(x, pos):
     return ((x >> pos) << (pos + 1)) | low
 
 
+def _swz(i, sh):
+    u = i >> sh
+    return i ^ ((((u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7) << sh)
+
+
+def run_pass_rs(state, p, rs_ops, pool, cdtype, n_local, index_offset=0):
+    """Register-stage form (csrc/rs_pass.cu): the tile lives in a swizzled shared-memory image and
+    is re-read per stage as a[thread][register combo]."""
+    T, L = p.tile_bits, p.low_bits
+    sh = 0 if np.dtype(cdtype).itemsize == 16 else 1
+    KR = T - 8
+    A = 2**KR
+    fixed = bin(p.fix_mask).count("1")
+    tiles = np.arange(2 ** (n_local - T - fixed), dtype=np.int64)
+    base = _gather(tiles, p.fseg, p.n_fseg) | p.fix_val
+    i = np.arange(2**T, dtype=np.int64)
+    spread = i & ((1 << L) - 1)
+    rr = i >> L
+    for j in range(p.n_high):
+        spread |= ((rr >> j) & 1) << p.high[j]
+    G = base[:, None] | spread[None, :]
+    sm = np.empty((len(tiles), 2**T), dtype=cdtype)
+    sm[:, _swz(i, sh)] = state[G]  # swizzled shared-memory image
+    gbase = base | index_offset
+    t = np.arange(256, dtype=np.int64)
+    r = np.arange(A, dtype=np.int64)
+    a = None
+    addr = None
+
+    def tab_len(op):
+        mask = 0
+        for sg in list(op.tseg)[: op.n_tseg] + list(op.xseg)[: op.n_xseg]:
+            mask |= ((1 << sg.width) - 1) << sg.dst
+        for k in range(A):
+            mask |= int(op.rt[k])
+        return mask + 1
+
+    for o in range(p.rs_begin, p.rs_begin + p.rs_count):
+        op = rs_ops[o]
+        if op.kind == _abi.QLS_RS_STAGE:
+            if a is not None:
+                sm[:, addr.reshape(-1)] = a.reshape(len(tiles), -1)
+            tb = _swz(_gather(t, op.tseg, op.n_tseg), sh)
+            rt = np.array([op.rt[k] for k in range(A)], dtype=np.int64)
+            addr = tb[:, None] ^ rt[None, :]
+            assert len(np.unique(addr)) == 2**T, "stage layout is not a permutation of the tile"
+            a = sm[:, addr.reshape(-1)].reshape(len(tiles), 256, A)
+            continue
+        act = (gbase & op.xc_mask) == op.xc_val
+        tok = (t & op.ctl_tmask) == op.ctl_tval
+        rok = (r & op.ctl_rmask) == op.ctl_rval
+        if op.kind in (_abi.QLS_RS_G1, _abi.QLS_RS_G2):
+            k = 1 if op.kind == _abi.QLS_RS_G1 else 2
+            M = np.frombuffer(pool, dtype=cdtype, count=4**k, offset=op.pool_off).reshape(2**k, 2**k)
+            regs = [op.r[j] for j in range(k)]
+            g = np.arange(A >> k, dtype=np.int64)
+            i0 = g.copy()
+            for q in regs:
+                i0 = _insert_zero(i0, q)
+            offs = np.array([sum(((c >> j) & 1) << regs[j] for j in range(k)) for c in range(2**k)])
+            cols = i0[:, None] | offs[None, :]
+            sub = a[:, :, cols]  # tiles x t x groups x 2^k
+            res = np.einsum("rc,xtgc->xtgr", M, sub)
+            ok = act[:, None, None, None] & tok[None, :, None, None] & rok[i0][None, None, :, None]
+            a[:, :, cols] = np.where(ok, res, sub).astype(cdtype)
+        elif op.kind == _abi.QLS_RS_DIAG:
+            table = np.frombuffer(pool, dtype=cdtype, count=tab_len(op), offset=op.pool_off)
+            rt = np.array([op.rt[k] for k in range(A)], dtype=np.int64)
+            ti = (_gather(gbase, op.xseg, op.n_xseg)[:, None, None] | _gather(t, op.tseg, op.n_tseg)[None, :, None]
+                  | rt[None, None, :])
+            ok = act[:, None, None] & tok[None, :, None] & rok[None, None, :]
+            a = np.where(ok, a * table[ti], a).astype(cdtype)
+        elif op.kind == _abi.QLS_RS_MUXRY:
+            table = np.frombuffer(pool, dtype=cdtype, count=tab_len(op), offset=op.pool_off)
+            rt = np.array([op.rt[k] for k in range(A)], dtype=np.int64)
+            q = op.r[0]
+            i0 = _insert_zero(np.arange(A // 2, dtype=np.int64), q)
+            i1 = i0 | (1 << q)
+            ti = (_gather(gbase, op.xseg, op.n_xseg)[:, None, None] | _gather(t, op.tseg, op.n_tseg)[None, :, None]
+                  | rt[i0][None, None, :])
+            cs = table[ti]
+            x, y = a[:, :, i0], a[:, :, i1]
+            ok = act[:, None, None] & tok[None, :, None] & rok[i0][None, None, :]
+            a[:, :, i0] = np.where(ok, cs.real * x - cs.imag * y, x).astype(cdtype)
+            a[:, :, i1] = np.where(ok, cs.imag * x + cs.real * y, y).astype(cdtype)
+        else:
+            raise ValueError(op.kind)
+    sm[:, addr.reshape(-1)] = a.reshape(len(tiles), -1)
+    state[G] = sm[:, _swz(i, sh)]
+
+
 def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0, params=None):
     T, L = p.tile_bits, p.low_bits
     fixed = bin(p.fix_mask).count("1")
@@ -131,7 +222,7 @@ def run_pass(state, p, ops, pool, cdtype, n_local, index_offset=0, params=None):
     _ = esz
 
 
-def run_program(lowered, psi0=None, index_offset=0, params=None):
+def run_program(lowered, psi0=None, index_offset=0, params=None, form="sweep"):
     """Evolve |0...0> (or ``psi0``) through a LoweredProgram; returns the final local state."""
     n = lowered.n_local
     cdtype = np.complex128 if lowered.dtype == "fp64" else np.complex64
@@ -150,7 +241,11 @@ def run_program(lowered, psi0=None, index_offset=0, params=None):
     for s in steps:
         if s.kind == "passes":
             for pi in range(s.pass_begin, s.pass_end):
-                run_pass(state, lowered.passes[pi], lowered.ops, pool, cdtype, n, index_offset, params)
+                ps = lowered.passes[pi]
+                if form == "rs" and ps.rs_count > 0:
+                    run_pass_rs(state, ps, lowered.rs_ops, pool, cdtype, n, index_offset)
+                else:
+                    run_pass(state, ps, lowered.ops, pool, cdtype, n, index_offset, params)
         elif s.kind == "gemm":
             nb = s.nb
             rows = np.arange(2 ** (n - nb), dtype=np.int64)

@@ -38,7 +38,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     import ctypes as C
 
-    assert C.sizeof(_abi.QlsOp) == 128 and C.sizeof(_abi.QlsPass) == 120 and C.sizeof(_abi.QlsSeg) == 4
+    assert C.sizeof(_abi.QlsOp) == 128 and C.sizeof(_abi.QlsPass) == 128 and C.sizeof(_abi.QlsSeg) == 4
+    assert C.sizeof(_abi.QlsRsOp) == 192
 
 
 def test_product_fails_loudly_without_gpu():

@@ -334,3 +334,45 @@ def test_vqls_4x4_default_ansatz(cuda_device, tmp_path, monkeypatch):
     assert width == 2 and depth > 0 and qasm.startswith("OPENQASM 3")
     rel = np.linalg.norm(model.classical_solution - x) / np.linalg.norm(model.classical_solution)
     assert rel < 0.2  # the reference's own acceptance gate (plotting.py:136-143)
+
+
+# ---- register-stage kernel (full-size tiles) --------------------------------------------------------
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_register_stage_kernel_random(cuda_device, seed, precision):
+    from qls_b200 import _abi
+    from qls_b200.lower import LoweringOptions, lower_circuit
+    from qls_b200.statevector import Statevector
+
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(13, 18))
+    qc = random_circuit(n, 80, rng, max_k=2)
+    opts = LoweringOptions(dtype=precision, max_high=int(rng.integers(2, 6)))
+    assert any(p.rs_stages > 0 for p in lower_circuit(qc, opts).pass_info)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    tol = TOL64 if precision == "fp64" else TOL32
+    got = Statevector(qc, precision=precision, options=opts).data
+    assert np.max(np.abs(got - want)) <= tol
+    lib = _abi.load()
+    lib.qls_set_sweep_only(1)
+    try:
+        sweep = Statevector(qc, precision=precision, options=LoweringOptions(dtype=precision, max_high=opts.max_high)).data
+    finally:
+        lib.qls_set_sweep_only(0)
+    assert np.max(np.abs(sweep - want)) <= tol
+    assert np.max(np.abs(sweep - got)) <= (1e-13 if precision == "fp64" else 1e-5)
+
+
+def test_register_stage_kernel_hhl_shaped_many_tiles(cuda_device):
+    """n = 22: 1024 tiles per pass, persistent CTAs loop over several tiles each."""
+    from qls_b200.statevector import Statevector
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    n = 22
+    qc = hhl_shaped_circuit(n)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = Statevector(qc).data
+    assert np.max(np.abs(got - want)) <= TOL64
+    assert _fidelity(got, want) >= FID

@@ -125,3 +125,45 @@ def test_sharded_index_offset_semantics():
     half = 2 ** (n - 1)
     got = np.concatenate([run_program(low, psi0[:half], 0), run_program(low, psi0[half:], half)])
     assert np.max(np.abs(got - want)) < 1e-12
+
+
+# ---- register-stage form (csrc/rs_pass.cu) ---------------------------------------------------
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("dtype", ["fp64", "fp32"])
+def test_register_stage_form_matches_oracle(seed, dtype):
+    rng = np.random.default_rng(900 + seed)
+    T = 12 if dtype == "fp64" else 13
+    n = T + int(rng.integers(0, 3))
+    qc = random_circuit(n, 40, rng, max_k=2)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    low = lower_circuit(qc, LoweringOptions(dtype=dtype, max_fuse_qubits=2, max_high=int(rng.integers(2, 6))))
+    assert any(p.rs_stages > 0 for p in low.pass_info)
+    got = run_program(low, form="rs")
+    tol = 1e-12 if dtype == "fp64" else 1e-5
+    assert np.max(np.abs(got - want)) < tol
+    assert np.max(np.abs(run_program(low, form="sweep") - want)) < tol
+
+
+def test_register_stage_form_of_hhl_shaped_circuit():
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    qc = hhl_shaped_circuit(14)
+    want = numpy_sv.run(14, circuit_to_stream(qc))
+    low = lower_circuit(qc, LoweringOptions(max_fuse_qubits=2))
+    assert any(p.rs_stages > 0 for p in low.pass_info)
+    assert np.max(np.abs(run_program(low, form="rs") - want)) < 1e-12
+    # at full size every pass of the benchmark circuit has the register-stage form
+    big = lower_circuit(hhl_shaped_circuit(33), LoweringOptions(max_fuse_qubits=2))
+    assert all(p.rs_stages > 0 for p in big.pass_info)
+
+
+def test_wide_dense_blocks_keep_the_sweep_form():
+    rng = np.random.default_rng(4)
+    from _util import random_unitary
+    qc = QuantumCircuit(13)
+    qc.h(3)
+    qc.unitary(random_unitary(3, rng), [1, 5, 12])
+    low = lower_circuit(qc, LoweringOptions())
+    assert all(p.rs_stages == 0 for p in low.pass_info)
