@@ -1,9 +1,9 @@
 // Register-stage tile-pass kernel (the fast path for full-size tiles).
 //
-// Persistent CTAs (2 per SM, 256 threads).  A tile of 2^T amplitudes (T = 12 complex128 /
-// 13 complex64 -> 64 KB) is staged into shared memory with 16-byte cp.async, then lives in the
-// registers of the CTA: every thread holds 2^KR amplitudes (KR = 4 / 5: the stage's "register
-// qubits"), the remaining 8 tile bits are the thread index.  All micro-ops of a stage -- 1- and
+// Persistent CTAs (2 per SM, 512 threads -> 32 warps per SM).  A tile of 2^T amplitudes (T = 12
+// complex128 / 13 complex64 -> 64 KB) is staged into shared memory with 16-byte cp.async, then
+// lives in the registers of the CTA: every thread holds 2^KR amplitudes (KR = 3 / 4: the stage's
+// "register qubits"), the remaining 9 tile bits are the thread index.  All micro-ops of a stage -- 1- and
 // 2-qubit dense blocks on register qubits, diagonal tables, multiplexed RY -- run on registers with
 // compile-time register indices; shared memory is touched only to load, to re-distribute the tile
 // between stages (one write + one read), and to write back.  The shared-memory image is XOR
@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_MAX_OPS = 128;
 constexpr int RS_MAX_STAGES = 24;
 
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
     qls_rs_pass_kernel(typename Vec2<R>::type* __restrict__ state, const RsLaunch rl, const QlsRsOp* __restrict__ rs_ops,
                        const unsigned char* __restrict__ pool) {
   using V = typename Vec2<R>::type;
-  static_assert(T - KR == 8, "256 threads index the non-register tile bits");
+  static_assert((1 << (T - KR)) == RS_THREADS, "the threads index the non-register tile bits");
   constexpr int A = 1 << KR;
   constexpr int SH = sizeof(V) == 16 ? 0 : 1;
   constexpr int APU = 1 << SH;           // amplitudes per 16-byte unit
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   uint4* sm16 = reinterpret_cast<uint4*>(smem_raw);
   QlsRsOp* sops = reinterpret_cast<QlsRsOp*>(smem_raw + (sizeof(V) << T));
   uint64_t* hoff = reinterpret_cast<uint64_t*>(sops + rl.n_rs);            // [1 << n_high]
-  uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << rl.n_high));    // [stages][256]
+  uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << rl.n_high));    // [stages][RS_THREADS]
 
   const int tid = threadIdx.x;
   const int L = rl.L;
@@ -340,6 +340,6 @@ bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, int n_local) {
 
 int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset,
                        cudaStream_t stream) {
-  if (prog->dtype == QLS_C128) return launch_rs<double, 12, 4>(prog, p, state, n_local, index_offset, stream);
-  return launch_rs<float, 13, 5>(prog, p, state, n_local, index_offset, stream);
+  if (prog->dtype == QLS_C128) return launch_rs<double, 12, 3>(prog, p, state, n_local, index_offset, stream);
+  return launch_rs<float, 13, 4>(prog, p, state, n_local, index_offset, stream);
 }

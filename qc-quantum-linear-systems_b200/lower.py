@@ -463,7 +463,7 @@ class _Emitter:
         self.ops: List[_abi.QlsOp] = []
         self.rs_ops: List[_abi.QlsRsOp] = []
         self.rs_T = 12 if opts.dtype == "fp64" else 13
-        self.rs_KR = self.rs_T - 8
+        self.rs_KR = self.rs_T - 9  # 512 threads index 9 tile bits; 2^KR amplitudes per thread
         self.pool = bytearray()
         self.pass_info: List[PassInfo] = []
         self.steps: List[Step] = []

@@ -1,0 +1,374 @@
+"""Sharded statevectors: states larger than one GPU's HBM (BASELINE.json configs[4]: 34/35/36
+qubits fp64 on 2/4/8 B200).
+
+Partition: rank = the top ``g = log2(world)`` *physical* index bits; every GPU holds a contiguous
+shard of ``2**(n-g)`` amplitudes.  A *layout* maps logical qubits to physical positions and changes
+over the circuit:
+
+* blocks that touch (act non-diagonally on) local positions only run as ordinary local programs;
+  controls, diagonal tables and RY selectors on global positions need no communication -- the
+  kernels read the rank bits from ``index_offset`` (SURVEY.md section 8e "no-comm cases");
+* when a block touches a global position the planner inserts a *remap*: global position ``G`` is
+  swapped with a local position ``l`` (pairwise exchange of half a shard with rank ``r ^ bit``),
+  choosing to bring in the qubits touched soonest and to evict the local qubits whose next touch
+  is farthest away (Belady), preferring high local positions so the pack/unpack kernels stream.
+
+Execution: each remap is chunked (``chunk_amps``) through two small scratch buffers so that a
+128 GiB shard is exchanged in place: pack chunk -> ``isend``/``irecv`` with the partner (NCCL over
+NVLink; gloo in the CPU tests) -> unpack into the slots the chunk vacated.
+
+The planner is host-only and backend-agnostic; the local engine is pluggable so that the same
+runner drives CUDA shards (``CudaShardEngine``) and the CPU stand-in used by the gloo tests.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .circuit import QuantumCircuit, flatten
+from .lower import Block, LoweredProgram, LoweringOptions, fuse, lower_blocks, normalise
+
+# --------------------------------------------------------------------------------------
+# planning
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class Segment:
+    kind: str  # "local" | "swap"
+    lowered: Optional[LoweredProgram] = None
+    pairs: List[Tuple[int, int]] = field(default_factory=list)  # swap: (global physical position, local position)
+
+
+@dataclass
+class ShardedPlan:
+    num_qubits: int
+    n_local: int
+    n_global: int
+    segments: List[Segment]
+    initial_layout: List[int]  # physical position of logical qubit q
+    final_layout: List[int]
+    amp_updates: int  # whole-state sum over fused blocks of 2^(n-c)
+    n_source_gates: int
+
+    @property
+    def n_swaps(self) -> int:
+        return sum(len(s.pairs) for s in self.segments if s.kind == "swap")
+
+
+def _relabel(b: Block, phys: Sequence[int]) -> Block:
+    """The same block on physical positions."""
+    nb = Block(b.kind, tuple(phys[q] for q in b.targets), {phys[q]: v for q, v in b.controls.items()}, b.matrix,
+               [(tuple(phys[q] for q in fq), ft) for fq, ft in b.factors], tuple(phys[q] for q in b.selectors),
+               b.angles, b.amps, b.param, b.n_source)
+    if b.kind == "diag":
+        # diag targets are kept sorted by the lowering
+        order = np.argsort(nb.targets)
+        nb.targets = tuple(nb.targets[i] for i in order)
+    return nb
+
+
+def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[LoweringOptions] = None,
+                 protect_low: int = 8) -> ShardedPlan:
+    g = int(round(math.log2(world_size)))
+    if 2**g != world_size:
+        raise ValueError("world size must be a power of two")
+    n = circuit.num_qubits
+    n_local = n - g
+    base = opts or LoweringOptions()
+    if n_local < 2:
+        raise ValueError("too few local qubits")
+    leaves, phase = flatten(circuit)
+    blocks = fuse(normalise(leaves), base.max_fuse_qubits, base.max_diag_qubits)
+    if phase:
+        ph = np.array([np.exp(1j * phase)])
+        if blocks and blocks[0].kind == "init":
+            b0 = blocks[0]
+            blocks[0] = Block("init", b0.targets, amps=b0.amps * ph[0])
+        else:
+            blocks.insert(0, Block("diag", (), factors=[((), ph)], n_source=0))
+    # next-touch table (Belady): for every block index, the next index at which each logical qubit is touched
+    inf = len(blocks) + 1
+    touch_at: List[List[int]] = [[] for _ in range(n)]
+    for i, b in enumerate(blocks):
+        for q in b.touched:
+            touch_at[q].append(i)
+
+    def next_touch(q: int, i: int) -> int:
+        for t in touch_at[q]:
+            if t >= i:
+                return t
+        return inf
+
+    phys = list(range(n))  # logical -> physical
+    # initial layout: the g logical qubits touched last start on the global positions, except that
+    # an initial state preparation keeps its register on the low local positions
+    pinned = set(blocks[0].targets) if blocks and blocks[0].kind == "init" else set()
+    order = sorted((q for q in range(n) if q not in pinned), key=lambda q: (-next_touch(q, 0), -q))
+    global_logical = sorted(order[:g])
+    rest = [q for q in range(n) if q not in global_logical]
+    for pos, q in enumerate(rest):
+        phys[q] = pos
+    for j, q in enumerate(global_logical):
+        phys[q] = n_local + j
+    initial = list(phys)
+
+    segments: List[Segment] = []
+    cur: List[Block] = []
+    amp_updates = 0
+
+    def close_local() -> None:
+        nonlocal cur
+        if cur:
+            o = LoweringOptions(**{**base.__dict__, "n_local": n_local})
+            segments.append(Segment("local", lowered=lower_blocks(n, cur, o)))
+            cur = []
+
+    for i, b in enumerate(blocks):
+        if b.kind != "init":
+            amp_updates += 2 ** (n - len(b.controls))
+        need_global = [q for q in b.touched if phys[q] >= n_local]
+        if need_global:
+            close_local()
+            where = {p: q for q, p in enumerate(phys)}
+            # bring in: every global qubit, soonest touch first (at least the ones this block needs)
+            incoming = sorted((q for q in range(n) if phys[q] >= n_local), key=lambda q: next_touch(q, i))
+            incoming = [q for q in incoming if q in need_global or next_touch(q, i) < inf]
+            # evict: local qubits with the farthest next touch, high positions first, never the low run
+            cands = [q for q in range(n) if protect_low <= phys[q] < n_local and q not in b.touched]
+            cands.sort(key=lambda q: (-next_touch(q, i), -phys[q]))
+            pairs = []
+            for qin in incoming:
+                if not cands:
+                    break
+                qout = cands[0]
+                if qin not in need_global and next_touch(qout, i) <= next_touch(qin, i):
+                    break  # not worth it
+                cands.pop(0)
+                pairs.append((phys[qin], phys[qout]))
+                phys[qin], phys[qout] = phys[qout], phys[qin]
+            if any(phys[q] >= n_local for q in b.touched):
+                raise ValueError("cannot make the block local (too few evictable qubits)")
+            segments.append(Segment("swap", pairs=pairs))
+            del where
+        cur.append(_relabel(b, phys))
+    close_local()
+    return ShardedPlan(n, n_local, g, segments, initial, list(phys), amp_updates, len(leaves))
+
+
+# --------------------------------------------------------------------------------------
+# execution
+# --------------------------------------------------------------------------------------
+
+
+class ShardedRunner:
+    """Drives one rank's shard through a plan.  ``engine`` supplies the local work:
+
+    ``run_local(lowered, initialise)``; ``pack(local_pos, bit, begin, count) -> tensor`` (a view of
+    engine-owned scratch); ``unpack(tensor, local_pos, bit, begin, count)``; ``recv_buffer(count)``;
+    ``half`` (amplitudes per slab = 2**(n_local-1))."""
+
+    def __init__(self, plan: ShardedPlan, engine: Any, rank: int, world: int, chunk_amps: int = 1 << 26, dist: Any = None):
+        self.plan, self.engine, self.rank, self.world = plan, engine, rank, world
+        self.chunk = int(chunk_amps)
+        if dist is None:
+            import torch.distributed as dist  # noqa: PLC0415
+        self.dist = dist
+        self.bytes_sent = 0
+
+    def run(self) -> None:
+        first = True
+        for seg in self.plan.segments:
+            if seg.kind == "local":
+                self.engine.run_local(seg.lowered, initialise=first)
+                first = False
+            else:
+                if first:
+                    raise ValueError("a plan cannot start with a remap")
+                for gpos, lpos in seg.pairs:
+                    self.swap(gpos - self.plan.n_local, lpos)
+
+    def swap(self, gbit: int, lpos: int) -> None:
+        """Exchange global position ``n_local + gbit`` with local position ``lpos``."""
+        dist = self.dist
+        partner = self.rank ^ (1 << gbit)
+        mine = (self.rank >> gbit) & 1
+        send_bit = 1 - mine  # the slab whose local bit differs from my rank bit moves
+        half = self.engine.half
+        for begin in range(0, half, self.chunk):
+            count = min(self.chunk, half - begin)
+            out = self.engine.pack(lpos, send_bit, begin, count)
+            inc = self.engine.recv_buffer(count)
+            ops = [dist.P2POp(dist.isend, out, partner), dist.P2POp(dist.irecv, inc, partner)]
+            if self.rank > partner:
+                ops.reverse()
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.engine.unpack(inc, lpos, send_bit, begin, count)
+            self.bytes_sent += out.numel() * out.element_size()
+
+
+class CudaShardEngine:
+    """One CUDA shard: DeviceState + per-segment DevicePrograms + two scratch chunks."""
+
+    def __init__(self, plan: ShardedPlan, rank: int, precision: str = "fp64", device: Optional[int] = None,
+                 chunk_amps: int = 1 << 26):
+        import torch
+
+        from . import _abi
+        from .engine import DeviceProgram, DeviceState
+
+        self._abi = _abi
+        self.torch = torch
+        self.plan = plan
+        self.rank = rank
+        self.state = DeviceState(plan.n_local, precision, device, index_offset=rank << plan.n_local)
+        self.half = 2 ** (plan.n_local - 1)
+        self.programs: Dict[int, DeviceProgram] = {}
+        for seg in plan.segments:
+            if seg.kind == "local":
+                self.programs[id(seg.lowered)] = DeviceProgram(seg.lowered, self.state.device)
+        chunk = min(int(chunk_amps), self.half)
+        with torch.cuda.device(self.state.device):
+            self._send = torch.empty(chunk, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
+            self._recv = torch.empty(chunk, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
+
+    def _stream(self) -> int:
+        return int(self.torch.cuda.current_stream().cuda_stream)
+
+    def run_local(self, lowered: LoweredProgram, initialise: bool) -> None:
+        self.programs[id(lowered)].run(self.state, initialise=initialise)
+
+    def pack(self, lpos: int, bit: int, begin: int, count: int):
+        st = self.state
+        with self.torch.cuda.device(st.device):
+            self._abi.check(st.lib.qls_pack_bit(st.ptr, self._send.data_ptr(), st.n_local, st.abi_dtype, lpos, bit, begin, count,
+                                                self._stream()))
+        return self._send[:count]
+
+    def recv_buffer(self, count: int):
+        return self._recv[:count]
+
+    def unpack(self, buf, lpos: int, bit: int, begin: int, count: int) -> None:
+        st = self.state
+        with self.torch.cuda.device(st.device):
+            self._abi.check(st.lib.qls_unpack_bit(st.ptr, buf.data_ptr(), st.n_local, st.abi_dtype, lpos, bit, begin, count,
+                                                  self._stream()))
+
+
+class ShardedShapedSolver:
+    """Multi-GPU counterpart of ``ShapedSolver`` (one process per GPU, ``torch.distributed`` is
+    initialised by the caller): ``solve(b_host)`` / ``run_device(b_dev)`` + ``reduce()``."""
+
+    def __init__(self, circuit: QuantumCircuit, nb: int, precision: str = "fp64", device: Optional[int] = None,
+                 options: Optional[LoweringOptions] = None, chunk_amps: int = 1 << 27):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        opts = options or LoweringOptions(dtype=precision)
+        opts.dtype = precision
+        self.n, self.nb = circuit.num_qubits, int(nb)
+        self.plan = plan_sharded(circuit, self.world, opts)
+        self.engine = CudaShardEngine(self.plan, self.rank, precision, device, chunk_amps)
+        self.runner = ShardedRunner(self.plan, self.engine, self.rank, self.world, chunk_amps, dist)
+        self.state = self.engine.state
+        first = self.plan.segments[0].lowered
+        if not (first.steps and first.steps[0].kind == "init"):
+            raise ValueError("circuit must start with a state preparation on the data register")
+        self._init_amps = first.steps[0].amps
+        self.lowered = first  # for accounting helpers (amp_bytes, n_local)
+        self.program = self.engine.programs[id(first)]
+        self.program.launches_per_run = sum(self.engine.programs[id(s.lowered)].launches_per_run
+                                            for s in self.plan.segments if s.kind == "local")
+
+    def amp_updates_global(self) -> int:
+        return self.plan.amp_updates
+
+    def total_pass_bytes_per_gpu(self) -> int:
+        return sum(s.lowered.total_pass_bytes() for s in self.plan.segments if s.kind == "local")
+
+    def _prepare(self, b_device=None, b_host=None) -> None:
+        self.state.init_basis(None)
+        if self.rank == 0:
+            if b_device is not None:
+                self.state.tensor[: 2**self.nb].copy_(b_device)
+            else:
+                self.state.write(0, self._init_amps if b_host is None else b_host)
+
+    def _run_segments(self) -> None:
+        first = True
+        for seg in self.plan.segments:
+            if seg.kind == "local":
+                self.engine.programs[id(seg.lowered)].run(self.state, initialise=False) if first is False else \
+                    self.engine.programs[id(seg.lowered)].run(self.state, initialise=False)
+                first = False
+            else:
+                for gpos, lpos in seg.pairs:
+                    self.runner.swap(gpos - self.plan.n_local, lpos)
+
+    def run_device(self, b_device=None) -> None:
+        self._prepare(b_device=b_device)
+        self._run_segments()
+
+    def _masks(self) -> Tuple[int, int, int, int]:
+        fl = self.plan.final_layout
+        flag = 1 << fl[self.n - 1]
+        nondata = 0
+        for q in range(self.nb, self.n):
+            nondata |= 1 << fl[q]
+        return flag, flag, nondata, flag
+
+    def reduce(self) -> Tuple[float, float]:
+        import torch
+
+        m1, v1, m2, v2 = self._masks()
+        p_flag = self.state.prob_mask(m1, v1)
+        norm_sq = self.state.prob_mask(m2, v2)
+        t = torch.tensor([p_flag, norm_sq], dtype=torch.float64, device=self.state.tensor.device)
+        self.dist.all_reduce(t)
+        out = t.tolist()
+        return float(out[0]), float(out[1])
+
+    def solve(self, b_host: np.ndarray):
+        import torch
+
+        self._prepare(b_host=np.asarray(b_host).reshape(-1))
+        self._run_segments()
+        p_flag, norm_sq = self.reduce()
+        # the solution slice: flag = 1, clock = 0, data = i, at the data qubits' final physical positions
+        fl = self.plan.final_layout
+        idx = np.zeros(2**self.nb, dtype=np.int64)
+        i = np.arange(2**self.nb, dtype=np.int64)
+        for q in range(self.nb):
+            idx |= ((i >> q) & 1) << fl[q]
+        idx |= 1 << fl[self.n - 1]
+        owner = idx >> self.plan.n_local
+        local = idx & (2**self.plan.n_local - 1)
+        x = torch.zeros(2**self.nb, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
+        sel = np.nonzero(owner == self.rank)[0]
+        if sel.size:
+            li = torch.from_numpy(local[sel]).to(self.state.tensor.device)
+            x[torch.from_numpy(sel).to(self.state.tensor.device)] = self.state.tensor[li]
+        xr = torch.view_as_real(x)
+        self.dist.all_reduce(xr)
+        return x.cpu().numpy(), p_flag, norm_sq
+
+    def time_passes(self, repeats: int = 1):
+        """Tile-pass kernel time per solve on this rank (CUDA events), launches, algorithmic bytes."""
+        tot, launches, nbytes = 0.0, 0, 0
+        for _ in range(repeats):
+            self._prepare()
+            launches, nbytes, ms = 0, 0, 0.0
+            for seg in self.plan.segments:
+                if seg.kind == "local":
+                    m, l, b = self.engine.programs[id(seg.lowered)].run_passes_timed(self.state)
+                    ms, launches, nbytes = ms + m, launches + l, nbytes + b
+                else:
+                    for gpos, lpos in seg.pairs:
+                        self.runner.swap(gpos - self.plan.n_local, lpos)
+            tot += ms
+        return tot / repeats, launches, nbytes

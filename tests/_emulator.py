@@ -33,8 +33,9 @@ def run_pass_rs(state, p, rs_ops, pool, cdtype, n_local, index_offset=0):
     is re-read per stage as a[thread][register combo]."""
     T, L = p.tile_bits, p.low_bits
     sh = 0 if np.dtype(cdtype).itemsize == 16 else 1
-    KR = T - 8
+    KR = T - 9
     A = 2**KR
+    NT = 2 ** (T - KR)
     fixed = bin(p.fix_mask).count("1")
     tiles = np.arange(2 ** (n_local - T - fixed), dtype=np.int64)
     base = _gather(tiles, p.fseg, p.n_fseg) | p.fix_val
@@ -47,7 +48,7 @@ def run_pass_rs(state, p, rs_ops, pool, cdtype, n_local, index_offset=0):
     sm = np.empty((len(tiles), 2**T), dtype=cdtype)
     sm[:, _swz(i, sh)] = state[G]  # swizzled shared-memory image
     gbase = base | index_offset
-    t = np.arange(256, dtype=np.int64)
+    t = np.arange(NT, dtype=np.int64)
     r = np.arange(A, dtype=np.int64)
     a = None
     addr = None
@@ -69,7 +70,7 @@ def run_pass_rs(state, p, rs_ops, pool, cdtype, n_local, index_offset=0):
             rt = np.array([op.rt[k] for k in range(A)], dtype=np.int64)
             addr = tb[:, None] ^ rt[None, :]
             assert len(np.unique(addr)) == 2**T, "stage layout is not a permutation of the tile"
-            a = sm[:, addr.reshape(-1)].reshape(len(tiles), 256, A)
+            a = sm[:, addr.reshape(-1)].reshape(len(tiles), NT, A)
             continue
         act = (gbase & op.xc_mask) == op.xc_val
         tok = (t & op.ctl_tmask) == op.ctl_tval
