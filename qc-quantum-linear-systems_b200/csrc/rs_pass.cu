@@ -1,9 +1,10 @@
 // Register-stage tile-pass kernel (the fast path for full-size tiles).
 //
-// Persistent CTAs (2 per SM, 512 threads -> 32 warps per SM).  A tile of 2^T amplitudes (T = 12
-// complex128 / 13 complex64 -> 64 KB) is staged into shared memory with 16-byte cp.async, then
-// lives in the registers of the CTA: every thread holds 2^KR amplitudes (KR = 3 / 4: the stage's
-// "register qubits"), the remaining 9 tile bits are the thread index.  All micro-ops of a stage -- 1- and
+// Persistent CTAs (2 per SM, 256 threads).  A tile of 2^T amplitudes (T = 12 complex128 /
+// 13 complex64 -> 64 KB) is staged into shared memory with 16-byte cp.async, then lives in the
+// registers of the CTA: every thread holds 2^KR amplitudes (KR = 4 / 5: the stage's "register
+// qubits"), the remaining 8 tile bits are the thread index.  (512 threads x 2^(KR-1) amplitudes was
+// measured slower: more stages per pass, see profiles/.)  All micro-ops of a stage -- 1- and
 // 2-qubit dense blocks on register qubits, diagonal tables, multiplexed RY -- run on registers with
 // compile-time register indices; shared memory is touched only to load, to re-distribute the tile
 // between stages (one write + one read), and to write back.  The shared-memory image is XOR
@@ -14,7 +15,7 @@
 
 namespace {
 
-constexpr int RS_THREADS = 512;
+constexpr int RS_THREADS = 256;
 constexpr int RS_MAX_OPS = 128;
 constexpr int RS_MAX_STAGES = 24;
 
@@ -33,6 +34,19 @@ __device__ __forceinline__ uint32_t swz(uint32_t i) {
   const uint32_t u = i >> SH;
   return i ^ ((((u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7u) << SH);
 }
+
+// address of register combination r: base ^ (xor of the per-qubit offsets of r's set bits); with a
+// compile-time r this folds into at most KR XORs on registers (no table lookups)
+template <int KR>
+__device__ __forceinline__ uint32_t rs_addr(uint32_t base, const uint32_t (&c)[KR], int r) {
+  uint32_t a = base;
+#pragma unroll
+  for (int j = 0; j < KR; ++j)
+    if ((r >> j) & 1) a ^= c[j];
+  return a;
+}
+
+constexpr uint32_t QLS_RS_FLAG_DIRECT = 0x10u;  // STAGE: every register qubit sits above the lane bits
 
 template <typename V, int A, int RQ, bool REAL>
 __device__ __forceinline__ void rs_g1(V (&a)[A], const V* __restrict__ M, bool tok, uint32_t rmask, uint32_t rval) {
@@ -194,8 +208,9 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   V* sm = reinterpret_cast<V*>(smem_raw);
   uint4* sm16 = reinterpret_cast<uint4*>(smem_raw);
   QlsRsOp* sops = reinterpret_cast<QlsRsOp*>(smem_raw + (sizeof(V) << T));
-  uint64_t* hoff = reinterpret_cast<uint64_t*>(sops + rl.n_rs);            // [1 << n_high]
-  uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << rl.n_high));    // [stages][RS_THREADS]
+  uint64_t* hoff = reinterpret_cast<uint64_t*>(sops + rl.n_rs);            // [1 << n_high] (+1: tile base slot)
+  uint64_t* s_base = hoff + (1 << rl.n_high);
+  uint16_t* ptb = reinterpret_cast<uint16_t*>(s_base + 2);                 // [stages][RS_THREADS]
 
   const int tid = threadIdx.x;
   const int L = rl.L;
@@ -221,39 +236,70 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   }
   __syncthreads();
 
-  // ---- persistent loop over tiles ------------------------------------------------------------------
-  for (uint64_t tile = blockIdx.x; tile < rl.n_tiles; tile += gridDim.x) {
-    const uint64_t base = gather_segs64(tile, rl.fseg, rl.n_fseg) | rl.fix_val;
-    const uint64_t gbase = base | rl.index_offset;
+  bool first_direct = false, last_direct = false;
+  if (rl.n_rs > 0) first_direct = (sops[0].flags & QLS_RS_FLAG_DIRECT) != 0;
+  for (int o = 0; o < rl.n_rs; ++o)
+    if (sops[o].kind == QLS_RS_STAGE) last_direct = (sops[o].flags & QLS_RS_FLAG_DIRECT) != 0;
 
+  // ---- persistent loop over tiles ------------------------------------------------------------------
+  // The tile counter -> base index deposit walks byte-sized segment descriptors in the kernel
+  // parameters; one thread does it per tile and publishes the result (every thread doing it cost
+  // more L1 traffic than the tile itself).
+  if (tid == 0) s_base[0] = gather_segs64((uint64_t)blockIdx.x, rl.fseg, rl.n_fseg) | rl.fix_val;
+  __syncthreads();
+  int parity = 0;
+  for (uint64_t tile = blockIdx.x; tile < rl.n_tiles; tile += gridDim.x) {
+    const uint64_t base = s_base[parity];
+    const uint64_t gbase = base | rl.index_offset;
+    if (tid == 0 && tile + gridDim.x < rl.n_tiles)
+      s_base[parity ^ 1] = gather_segs64(tile + gridDim.x, rl.fseg, rl.n_fseg) | rl.fix_val;  // visible after the syncs below
+    parity ^= 1;
+
+    if (!first_direct) {
 #pragma unroll 4
-    for (int u = tid; u < UNITS; u += RS_THREADS) {
-      const int i = u * APU;
-      const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
-      cp_async16(&sm16[swz<SH>((uint32_t)i) >> SH], &state[g]);
+      for (int u = tid; u < UNITS; u += RS_THREADS) {
+        const int i = u * APU;
+        const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
+        cp_async16(&sm16[swz<SH>((uint32_t)i) >> SH], &state[g]);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
     }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
 
     V a[A];
     int stage = -1;
     uint32_t mytb = 0;
-    const QlsRsOp* cur = nullptr;
+    uint32_t cq[KR];  // swizzled shared-memory offset of each register qubit of the current stage
+    uint32_t lq[KR];  // its tile-local bit
     for (int o = 0; o < rl.n_rs; ++o) {
       const QlsRsOp& op = sops[o];
       if (op.kind == QLS_RS_STAGE) {
         if (stage >= 0) {
 #pragma unroll
-          for (int r = 0; r < A; ++r) sm[mytb ^ cur->rt[r]] = a[r];
+          for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
           __syncthreads();
         }
         ++stage;
-        cur = &op;
         mytb = ptb[stage * RS_THREADS + tid];
 #pragma unroll
-        for (int r = 0; r < A; ++r) a[r] = sm[mytb ^ op.rt[r]];
-        __syncthreads();
+        for (int j = 0; j < KR; ++j) {
+          lq[j] = 1u << (j < 4 ? op.r[j] : op.pad0);
+          cq[j] = swz<SH>(lq[j]);
+        }
+        if (stage == 0 && first_direct) {
+          // all register qubits sit above the 5 lane bits: every warp load is 512 contiguous bytes
+          const uint32_t ltb = swz<SH>(mytb);  // the swizzle is an involution
+#pragma unroll
+          for (int r = 0; r < A; ++r) {
+            const uint32_t idx = rs_addr<KR>(ltb, lq, r);
+            a[r] = state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]];
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
+          __syncthreads();
+        }
         continue;
       }
       if ((gbase & op.xc_mask) != op.xc_val) continue;  // block-uniform
@@ -278,17 +324,25 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
         }
       }
     }
+    if (last_direct) {
+      const uint32_t ltb = swz<SH>(mytb);
 #pragma unroll
-    for (int r = 0; r < A; ++r) sm[mytb ^ cur->rt[r]] = a[r];
-    __syncthreads();
-
+      for (int r = 0; r < A; ++r) {
+        const uint32_t idx = rs_addr<KR>(ltb, lq, r);
+        state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]] = a[r];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
+      __syncthreads();
 #pragma unroll 4
-    for (int u = tid; u < UNITS; u += RS_THREADS) {
-      const int i = u * APU;
-      const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
-      *reinterpret_cast<uint4*>(&state[g]) = sm16[swz<SH>((uint32_t)i) >> SH];
+      for (int u = tid; u < UNITS; u += RS_THREADS) {
+        const int i = u * APU;
+        const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
+        *reinterpret_cast<uint4*>(&state[g]) = sm16[swz<SH>((uint32_t)i) >> SH];
+      }
     }
-    __syncthreads();  // the next tile's cp.async must not overtake these reads
+    __syncthreads();  // smem image and s_base slot are free for the next tile
   }
 }
 
@@ -311,7 +365,7 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, void* state, int n_local
   rl.n_tiles = 1ull << free_bits;
   int n_stages = p.pad >> 8;  // counted by qls_program_create
   const size_t smem = ((size_t)sizeof(V) << T) + (size_t)p.rs_count * sizeof(QlsRsOp) + (sizeof(uint64_t) << p.n_high) +
-                      (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
+                      2 * sizeof(uint64_t) + (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
   QLS_ARG(smem <= 112 * 1024, "register-stage pass needs %zu bytes of shared memory", smem);
   auto kern = qls_rs_pass_kernel<R, T, KR>;
   static bool attr_set[64] = {false};
@@ -340,6 +394,6 @@ bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, int n_local) {
 
 int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset,
                        cudaStream_t stream) {
-  if (prog->dtype == QLS_C128) return launch_rs<double, 12, 3>(prog, p, state, n_local, index_offset, stream);
-  return launch_rs<float, 13, 4>(prog, p, state, n_local, index_offset, stream);
+  if (prog->dtype == QLS_C128) return launch_rs<double, 12, 4>(prog, p, state, n_local, index_offset, stream);
+  return launch_rs<float, 13, 5>(prog, p, state, n_local, index_offset, stream);
 }

@@ -28,8 +28,19 @@ __global__ void __launch_bounds__(THREADS, HEAVY ? 2 : 3)
   const int tid = threadIdx.x;
   const int T = tl.T, L = tl.L;
 
-  // tile counter -> local base index (tile bits zero, pass-level control bits fixed)
-  const uint64_t base = gather_segs64((uint64_t)blockIdx.x, tl.fseg, tl.n_fseg) | tl.fix_val;
+  // Per-CTA index tables (the descriptors are byte arrays in the kernel parameters: walking
+  // them per amplitude costs more L1 traffic than the tile): hoff[r] = spread of the high-qubit
+  // combination r, s_base = this tile's base index (tile bits zero, pass-level controls fixed).
+  uint64_t* hoff = reinterpret_cast<uint64_t*>(smem_raw + (sizeof(V) << T));
+  uint64_t* s_base = hoff + (1 << tl.n_high);
+  for (int r = tid; r < (1 << tl.n_high); r += THREADS) {
+    uint64_t g = 0;
+    for (int j = 0; j < tl.n_high; ++j) g |= (uint64_t)((r >> j) & 1) << tl.high[j];
+    hoff[r] = g;
+  }
+  if (tid == 0) s_base[0] = gather_segs64((uint64_t)blockIdx.x, tl.fseg, tl.n_fseg) | tl.fix_val;
+  __syncthreads();
+  const uint64_t base = s_base[0];
 
   // 16-byte units: one complex128 or two complex64
   constexpr int APU = 16 / (int)sizeof(V);      // amplitudes per unit
@@ -39,11 +50,7 @@ __global__ void __launch_bounds__(THREADS, HEAVY ? 2 : 3)
 
   for (int u = tid; u < units; u += THREADS) {
     const int i = u * APU;
-    uint64_t g = base | (uint64_t)(i & lmask);
-    const int r = i >> L;
-#pragma unroll
-    for (int j = 0; j < QLS_MAX_HIGH; ++j)
-      if (j < tl.n_high) g |= (uint64_t)((r >> j) & 1) << tl.high[j];
+    const uint64_t g = base | (uint64_t)(i & lmask) | hoff[i >> L];
     cp_async16(&sm16[u], &state[g]);
   }
   cp_async_commit();
@@ -54,11 +61,7 @@ __global__ void __launch_bounds__(THREADS, HEAVY ? 2 : 3)
 
   for (int u = tid; u < units; u += THREADS) {
     const int i = u * APU;
-    uint64_t g = base | (uint64_t)(i & lmask);
-    const int r = i >> L;
-#pragma unroll
-    for (int j = 0; j < QLS_MAX_HIGH; ++j)
-      if (j < tl.n_high) g |= (uint64_t)((r >> j) & 1) << tl.high[j];
+    const uint64_t g = base | (uint64_t)(i & lmask) | hoff[i >> L];
     *reinterpret_cast<uint4*>(&state[g]) = sm16[u];
   }
 }
@@ -84,7 +87,7 @@ static int launch_pass(const QlsProgram* prog, const QlsPass& p, void* state, in
   const int fixed = __builtin_popcountll(p.fix_mask);
   const int free_bits = n_local - p.tile_bits - fixed;
   QLS_ARG(free_bits >= 0 && free_bits < 31, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
-  const size_t smem = (size_t)sizeof(V) << p.tile_bits;
+  const size_t smem = ((size_t)sizeof(V) << p.tile_bits) + (sizeof(uint64_t) << p.n_high) + 2 * sizeof(uint64_t);
   auto kern = qls_tile_pass_kernel<R, THREADS, HEAVY>;
   static bool attr_set[64] = {false};  // per template instantiation and device
   if (!attr_set[prog->device & 63]) {

@@ -463,7 +463,7 @@ class _Emitter:
         self.ops: List[_abi.QlsOp] = []
         self.rs_ops: List[_abi.QlsRsOp] = []
         self.rs_T = 12 if opts.dtype == "fp64" else 13
-        self.rs_KR = self.rs_T - 9  # 512 threads index 9 tile bits; 2^KR amplitudes per thread
+        self.rs_KR = self.rs_T - 8  # 256 threads index 8 tile bits; 2^KR amplitudes per thread
         self.pool = bytearray()
         self.pass_info: List[PassInfo] = []
         self.steps: List[Step] = []
@@ -675,6 +675,10 @@ class _Emitter:
                 st.kind = _abi.QLS_RS_STAGE
                 for j, p_ in enumerate(regq_sorted[:4]):
                     st.r[j] = p_
+                if KR > 4:
+                    st.pad0 = regq_sorted[4]
+                if min(regq_sorted) >= 5:
+                    st.flags |= 0x10  # direct global <-> register access is coalesced (lanes = tile bits 0..4)
                 segs = _segments([(j, p_) for j, p_ in enumerate(tpos)])
                 if len(segs) > _abi.QLS_MAX_SEG:
                     raise _RsUnsupported("thread deposit needs too many segments")
