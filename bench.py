@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "hhl_amp_updates_per_s"
+TRAFFIC_NOTE = None  # dram bytes per launch from an ncu --set full capture: see profiles/README.md
 UNIT = "amp-updates/s"
 
 
@@ -273,13 +274,12 @@ def run_gpu(args):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        n_tile = low.n_passes
-        pass_bytes = low.total_pass_bytes()
+        st = solver.stats()
         roofline = None
         if kern_ms:
             achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": "qls_tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                        "frac": achieved / peak, "peak_source": peak_src, "traffic": TRAFFIC_NOTE,
                         "launches_per_step": kern_launches, "algorithmic_bytes_per_step": kern_bytes,
                         "avg_launch_ms": kern_ms / max(1, kern_launches), "kernel_ms_per_step": kern_ms}
         # CPU baseline on a bounded sample of the same workload
@@ -288,21 +288,32 @@ def run_gpu(args):
                "sample": f"same circuit at n={args.cpu_qubits} ({leaves} unfused leaf gates through oracle/numpy_sv.py, "
                          f"{sec_cpu:.2f} s); per-amplitude cost is size independent"}
         launches_per_step = solver.program.launches_per_run + 2 + 4  # + init fill/copy + two 2-kernel reductions
+        remap = None
+        if world > 1:
+            sent = st["remap_bytes_sent_per_gpu"]
+            ms = getattr(solver, "remap_ms", 0.0)
+            launches_per_step += 2 * st["remaps"] * max(1, (S << (low.n_local - 1)) // (S * solver.runner.chunk))
+            remap = {"remaps_per_step": st["remaps"], "bytes_sent_per_gpu": sent, "ms_per_step": ms,
+                     "achieved_gbs_per_direction": (sent / (ms * 1e-3) / 1e9) if ms else None, "peak": 770.0,
+                     "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
+                     "frac": (sent / (ms * 1e-3) / 1e9 / 770.0) if ms else None,
+                     "includes": "pack + NCCL send/recv + unpack, chunked, not overlapped with compute"}
         line = {
             "metric": METRIC, "value": amp_updates / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "config": {"workload": f"hhl_shaped_n{n}" + (f"_sharded_{world}gpu" if world > 1 else ""),
                        "n_qubits": n, "nb": nb, "nl": n - 1 - nb, "state_bytes_per_gpu": S << low.n_local,
-                       "fused_passes": n_tile, "fused_blocks": int(sum(p.n_ops for p in low.pass_info)),
-                       "source_gates": low.n_source_gates, "amp_updates_per_step": amp_updates,
-                       "hbm_bytes_per_step": pass_bytes + (S << low.n_local),
+                       "fused_passes": st["fused_passes"], "fused_blocks": st["fused_blocks"],
+                       "source_gates": st["source_gates"], "amp_updates_per_step": amp_updates,
+                       "hbm_bytes_per_step_per_gpu": st["pass_bytes_per_gpu"] + (S << low.n_local),
                        "l2_policy": "inputs_larger_than_L2" if (S << low.n_local) > (256 << 20) else "state_fits_L2_no_flush",
                        "program": "lowered once outside the timed region; b differs per solve only through init"},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": amp_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(b_host.nbytes), "d2h_bytes_per_step": int(x.nbytes) + 2 * 16,
                     "api": "ShapedSolver.solve(b_host) -> (x_host, P(flag=1), |x|^2)"},
+            "remap": remap,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "result_check": {"p_flag1": last[0], "norm_sq": last[1], "e2e_p_flag1": p_flag},

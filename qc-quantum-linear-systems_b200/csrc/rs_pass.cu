@@ -75,7 +75,7 @@ __device__ __forceinline__ void rs_g1(V (&a)[A], const V* __restrict__ M, bool t
   }
 }
 
-template <typename V, int A, int R1, int R2>
+template <typename V, int A, int R1, int R2, bool REAL>
 __device__ __forceinline__ void rs_g2(V (&a)[A], const V* __restrict__ M, bool tok, uint32_t rmask, uint32_t rval) {
   static_assert(R1 < R2, "register qubits must be ascending");
 #pragma unroll
@@ -88,10 +88,16 @@ __device__ __forceinline__ void rs_g2(V (&a)[A], const V* __restrict__ M, bool t
       V o[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        o[r] = cmul(__ldg(M + 4 * r), x0);
-        cfma(o[r], __ldg(M + 4 * r + 1), x1);
-        cfma(o[r], __ldg(M + 4 * r + 2), x2);
-        cfma(o[r], __ldg(M + 4 * r + 3), x3);
+        if (REAL) {  // H (x) H, CX, RY (x) RY ...: half the multiplies
+          const V m0 = __ldg(M + 4 * r), m1 = __ldg(M + 4 * r + 1), m2 = __ldg(M + 4 * r + 2), m3 = __ldg(M + 4 * r + 3);
+          o[r].x = fma(m3.x, x3.x, fma(m2.x, x2.x, fma(m1.x, x1.x, m0.x * x0.x)));
+          o[r].y = fma(m3.x, x3.y, fma(m2.x, x2.y, fma(m1.x, x1.y, m0.x * x0.y)));
+        } else {
+          o[r] = cmul(__ldg(M + 4 * r), x0);
+          cfma(o[r], __ldg(M + 4 * r + 1), x1);
+          cfma(o[r], __ldg(M + 4 * r + 2), x2);
+          cfma(o[r], __ldg(M + 4 * r + 3), x3);
+        }
       }
       a[i00] = o[0];
       a[i01] = o[1];
@@ -101,22 +107,41 @@ __device__ __forceinline__ void rs_g2(V (&a)[A], const V* __restrict__ M, bool t
   }
 }
 
-template <typename V, int A>
+// table-index contribution of register combination r = OR of the per-register-qubit contributions
+// (op.rt[1 << j]); with a compile-time r this folds into at most KR ORs on registers
+template <int KR>
+__device__ __forceinline__ uint32_t rs_tidx(uint32_t base, const uint32_t (&d)[KR], int r) {
+  uint32_t t = base;
+#pragma unroll
+  for (int j = 0; j < KR; ++j)
+    if ((r >> j) & 1) t |= d[j];
+  return t;
+}
+
+template <typename V, int A, int KR>
 __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
+  uint32_t d[KR];
+#pragma unroll
+  for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
+  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
 #pragma unroll
   for (int r = 0; r < A; ++r) {
-    if (tok && (((uint32_t)r & op.ctl_rmask) == op.ctl_rval)) a[r] = cmul(a[r], __ldg(&table[ti0 | op.rt[r]]));
+    if (tok && (((uint32_t)r & rm) == rv)) a[r] = cmul(a[r], __ldg(&table[rs_tidx<KR>(ti0, d, r)]));
   }
 }
 
-template <typename V, int A, int RQ>
+template <typename V, int A, int KR, int RQ>
 __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
+  uint32_t d[KR];
+#pragma unroll
+  for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
+  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
 #pragma unroll
   for (int p = 0; p < A / 2; ++p) {
     const int i0 = ((p >> RQ) << (RQ + 1)) | (p & ((1 << RQ) - 1));
     const int i1 = i0 | (1 << RQ);
-    if (tok && (((uint32_t)i0 & op.ctl_rmask) == op.ctl_rval)) {
-      const V cs = __ldg(&table[ti0 | op.rt[i0]]);
+    if (tok && (((uint32_t)i0 & rm) == rv)) {
+      const V cs = __ldg(&table[rs_tidx<KR>(ti0, d, i0)]);
       const V x = a[i0], y = a[i1];
       V b0, b1;
       b0.x = cs.x * x.x - cs.y * y.x;
@@ -156,9 +181,11 @@ __device__ __forceinline__ void rs_dispatch_g1(V (&a)[A], const QlsRsOp& op, con
 template <typename V, int A, int KR>
 __device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
-#define QLS_G2_CASE(p, q) \
-  case (p * 8 + q):       \
-    rs_g2<V, A, p, q>(a, M, tok, rm, rv); \
+  const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
+#define QLS_G2_CASE(p, q)                                   \
+  case (p * 8 + q):                                         \
+    if (real) rs_g2<V, A, p, q, true>(a, M, tok, rm, rv);   \
+    else rs_g2<V, A, p, q, false>(a, M, tok, rm, rv);       \
     break;
   switch (op.r[0] * 8 + op.r[1]) {
     QLS_G2_CASE(0, 1)
@@ -170,10 +197,10 @@ __device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, con
     default:
       if constexpr (KR >= 5) {
         switch (op.r[0]) {
-          case 0: rs_g2<V, A, 0, 4>(a, M, tok, rm, rv); break;
-          case 1: rs_g2<V, A, 1, 4>(a, M, tok, rm, rv); break;
-          case 2: rs_g2<V, A, 2, 4>(a, M, tok, rm, rv); break;
-          case 3: rs_g2<V, A, 3, 4>(a, M, tok, rm, rv); break;
+          case 0: if (real) rs_g2<V, A, 0, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 0, 4, false>(a, M, tok, rm, rv); break;
+          case 1: if (real) rs_g2<V, A, 1, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 1, 4, false>(a, M, tok, rm, rv); break;
+          case 2: if (real) rs_g2<V, A, 2, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 2, 4, false>(a, M, tok, rm, rv); break;
+          case 3: if (real) rs_g2<V, A, 3, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 3, 4, false>(a, M, tok, rm, rv); break;
         }
       }
       break;
@@ -184,12 +211,12 @@ __device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, con
 template <typename V, int A, int KR>
 __device__ __forceinline__ void rs_dispatch_muxry(V (&a)[A], const QlsRsOp& op, const V* table, uint32_t ti0, bool tok) {
   switch (op.r[0]) {
-    case 0: rs_muxry<V, A, 0>(a, op, table, ti0, tok); break;
-    case 1: rs_muxry<V, A, 1>(a, op, table, ti0, tok); break;
-    case 2: rs_muxry<V, A, 2>(a, op, table, ti0, tok); break;
-    case 3: rs_muxry<V, A, 3>(a, op, table, ti0, tok); break;
+    case 0: rs_muxry<V, A, KR, 0>(a, op, table, ti0, tok); break;
+    case 1: rs_muxry<V, A, KR, 1>(a, op, table, ti0, tok); break;
+    case 2: rs_muxry<V, A, KR, 2>(a, op, table, ti0, tok); break;
+    case 3: rs_muxry<V, A, KR, 3>(a, op, table, ti0, tok); break;
     case 4:
-      if constexpr (KR >= 5) rs_muxry<V, A, 4>(a, op, table, ti0, tok);
+      if constexpr (KR >= 5) rs_muxry<V, A, KR, 4>(a, op, table, ti0, tok);
       break;
   }
 }
@@ -314,7 +341,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
           break;
         case QLS_RS_DIAG: {
           const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
-          rs_diag<V, A>(a, op, data, ti0, tok);
+          rs_diag<V, A, KR>(a, op, data, ti0, tok);
           break;
         }
         case QLS_RS_MUXRY: {

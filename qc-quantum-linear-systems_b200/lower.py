@@ -756,6 +756,8 @@ class _Emitter:
                     m = _permute_matrix(m, [1, 0])
                     regs = [regs[1], regs[0]]
                 op.r[0], op.r[1] = regs
+                if not np.any(m.imag):
+                    op.flags |= _abi.QLS_OP_FLAG_REAL
             op.pool_off = self._pool_add(m)
             self._rs_controls(op, b.controls, local_pos, rho, tbit)
             yield op

@@ -192,23 +192,36 @@ class ShardedRunner:
                     self.swap(gpos - self.plan.n_local, lpos)
 
     def swap(self, gbit: int, lpos: int) -> None:
-        """Exchange global position ``n_local + gbit`` with local position ``lpos``."""
+        """Exchange global position ``n_local + gbit`` with local position ``lpos``.
+
+        Software pipeline over chunks with two scratch slots: while chunk ``i`` is on the wire,
+        chunk ``i+1`` is packed and chunk ``i-1`` is unpacked (the exchange depends only on its own
+        pack; NCCL runs on its own stream)."""
         dist = self.dist
         partner = self.rank ^ (1 << gbit)
         mine = (self.rank >> gbit) & 1
         send_bit = 1 - mine  # the slab whose local bit differs from my rank bit moves
         half = self.engine.half
-        for begin in range(0, half, self.chunk):
-            count = min(self.chunk, half - begin)
-            out = self.engine.pack(lpos, send_bit, begin, count)
-            inc = self.engine.recv_buffer(count)
+        chunks = [(b, min(self.chunk, half - b)) for b in range(0, half, self.chunk)]
+
+        def start(i: int):
+            begin, count = chunks[i]
+            out = self.engine.pack(lpos, send_bit, begin, count, slot=i & 1)
+            inc = self.engine.recv_buffer(count, slot=i & 1)
             ops = [dist.P2POp(dist.isend, out, partner), dist.P2POp(dist.irecv, inc, partner)]
             if self.rank > partner:
                 ops.reverse()
-            for req in dist.batch_isend_irecv(ops):
+            self.bytes_sent += out.numel() * out.element_size()
+            return dist.batch_isend_irecv(ops), inc
+
+        inflight = start(0)
+        for i, (begin, count) in enumerate(chunks):
+            nxt = start(i + 1) if i + 1 < len(chunks) else None
+            reqs, inc = inflight
+            for req in reqs:
                 req.wait()
             self.engine.unpack(inc, lpos, send_bit, begin, count)
-            self.bytes_sent += out.numel() * out.element_size()
+            inflight = nxt
 
 
 class CudaShardEngine:
@@ -233,8 +246,8 @@ class CudaShardEngine:
                 self.programs[id(seg.lowered)] = DeviceProgram(seg.lowered, self.state.device)
         chunk = min(int(chunk_amps), self.half)
         with torch.cuda.device(self.state.device):
-            self._send = torch.empty(chunk, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
-            self._recv = torch.empty(chunk, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
+            self._send = [torch.empty(chunk, dtype=self.state.tensor.dtype, device=self.state.tensor.device) for _ in range(2)]
+            self._recv = [torch.empty(chunk, dtype=self.state.tensor.dtype, device=self.state.tensor.device) for _ in range(2)]
 
     def _stream(self) -> int:
         return int(self.torch.cuda.current_stream().cuda_stream)
@@ -242,15 +255,15 @@ class CudaShardEngine:
     def run_local(self, lowered: LoweredProgram, initialise: bool) -> None:
         self.programs[id(lowered)].run(self.state, initialise=initialise)
 
-    def pack(self, lpos: int, bit: int, begin: int, count: int):
+    def pack(self, lpos: int, bit: int, begin: int, count: int, slot: int = 0):
         st = self.state
         with self.torch.cuda.device(st.device):
-            self._abi.check(st.lib.qls_pack_bit(st.ptr, self._send.data_ptr(), st.n_local, st.abi_dtype, lpos, bit, begin, count,
-                                                self._stream()))
-        return self._send[:count]
+            self._abi.check(st.lib.qls_pack_bit(st.ptr, self._send[slot].data_ptr(), st.n_local, st.abi_dtype, lpos, bit, begin,
+                                                count, self._stream()))
+        return self._send[slot][:count]
 
-    def recv_buffer(self, count: int):
-        return self._recv[:count]
+    def recv_buffer(self, count: int, slot: int = 0):
+        return self._recv[slot][:count]
 
     def unpack(self, buf, lpos: int, bit: int, begin: int, count: int) -> None:
         st = self.state
@@ -300,12 +313,9 @@ class ShardedShapedSolver:
                 self.state.write(0, self._init_amps if b_host is None else b_host)
 
     def _run_segments(self) -> None:
-        first = True
         for seg in self.plan.segments:
             if seg.kind == "local":
-                self.engine.programs[id(seg.lowered)].run(self.state, initialise=False) if first is False else \
-                    self.engine.programs[id(seg.lowered)].run(self.state, initialise=False)
-                first = False
+                self.engine.programs[id(seg.lowered)].run(self.state, initialise=False)  # state prepared by _prepare
             else:
                 for gpos, lpos in seg.pairs:
                     self.runner.swap(gpos - self.plan.n_local, lpos)
@@ -357,9 +367,23 @@ class ShardedShapedSolver:
         self.dist.all_reduce(xr)
         return x.cpu().numpy(), p_flag, norm_sq
 
+    def stats(self) -> Dict[str, int]:
+        local = [s.lowered for s in self.plan.segments if s.kind == "local"]
+        return {
+            "fused_passes": sum(l.n_passes for l in local),
+            "fused_blocks": sum(sum(len(p.op_controls) for p in l.pass_info) for l in local),
+            "source_gates": self.plan.n_source_gates,
+            "pass_bytes_per_gpu": sum(l.total_pass_bytes() for l in local),
+            "remaps": self.plan.n_swaps,
+            "remap_bytes_sent_per_gpu": self.plan.n_swaps * self.engine.half * self.lowered.amp_bytes(),
+        }
+
     def time_passes(self, repeats: int = 1):
-        """Tile-pass kernel time per solve on this rank (CUDA events), launches, algorithmic bytes."""
-        tot, launches, nbytes = 0.0, 0, 0
+        """Tile-pass kernel time per solve on this rank (CUDA events), launches, algorithmic bytes.
+        Also records ``self.remap_ms``: event time of the remaps (pack + send/recv + unpack)."""
+        import torch
+
+        tot, launches, nbytes, remap = 0.0, 0, 0, 0.0
         for _ in range(repeats):
             self._prepare()
             launches, nbytes, ms = 0, 0, 0.0
@@ -368,7 +392,13 @@ class ShardedShapedSolver:
                     m, l, b = self.engine.programs[id(seg.lowered)].run_passes_timed(self.state)
                     ms, launches, nbytes = ms + m, launches + l, nbytes + b
                 else:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                     for gpos, lpos in seg.pairs:
                         self.runner.swap(gpos - self.plan.n_local, lpos)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    remap += e0.elapsed_time(e1)
             tot += ms
+        self.remap_ms = remap / repeats
         return tot / repeats, launches, nbytes

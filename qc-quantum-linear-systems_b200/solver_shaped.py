@@ -50,6 +50,17 @@ class ShapedSolver:
     def _run_rest(self) -> None:
         self.program.run(self.state, initialise=False)  # step 0 (state preparation) is done above
 
+    def stats(self):
+        low = self.lowered
+        return {
+            "fused_passes": low.n_passes,
+            "fused_blocks": sum(len(p.op_controls) for p in low.pass_info),
+            "source_gates": low.n_source_gates,
+            "pass_bytes_per_gpu": low.total_pass_bytes(),
+            "remaps": 0,
+            "remap_bytes_sent_per_gpu": 0,
+        }
+
     def time_passes(self, repeats: int = 1):
         """(ms, launches, algorithmic bytes) of the tile-pass kernels per solve, timed with CUDA
         events on the launching stream (the roofline numerator of bench.py)."""

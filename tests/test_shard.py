@@ -54,10 +54,10 @@ class NumpyShardEngine:
         j = np.arange(begin, begin + count, dtype=np.int64)
         return ((j >> lpos) << (lpos + 1)) | (bit << lpos) | (j & ((1 << lpos) - 1))
 
-    def pack(self, lpos, bit, begin, count):
+    def pack(self, lpos, bit, begin, count, slot=0):
         return self.torch.from_numpy(self.state[self._slab_index(lpos, bit, begin, count)].copy())
 
-    def recv_buffer(self, count):
+    def recv_buffer(self, count, slot=0):
         return self.torch.empty(count, dtype=self.torch.complex128)
 
     def unpack(self, buf, lpos, bit, begin, count):
