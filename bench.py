@@ -282,11 +282,13 @@ def run_gpu(args):
                         "frac": achieved / peak, "peak_source": peak_src, "traffic": TRAFFIC_NOTE,
                         "launches_per_step": kern_launches, "algorithmic_bytes_per_step": kern_bytes,
                         "avg_launch_ms": kern_ms / max(1, kern_launches), "kernel_ms_per_step": kern_ms}
-        # CPU baseline on a bounded sample of the same workload
-        job_cpu, sec_cpu, leaves = cpu_reference_sample(args.cpu_qubits)
-        cpu = {"value": job_cpu / sec_cpu, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"same circuit at n={args.cpu_qubits} ({leaves} unfused leaf gates through oracle/numpy_sv.py, "
-                         f"{sec_cpu:.2f} s); per-amplitude cost is size independent"}
+        # CPU baseline on a bounded sample of the same workload (N = 1 only: torchrun pins OMP threads to 1)
+        cpu = None
+        if world == 1:
+            job_cpu, sec_cpu, leaves = cpu_reference_sample(args.cpu_qubits)
+            cpu = {"value": job_cpu / sec_cpu, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"same circuit at n={args.cpu_qubits} ({leaves} unfused leaf gates through oracle/numpy_sv.py, "
+                             f"{sec_cpu:.2f} s); per-amplitude cost is size independent"}
         launches_per_step = solver.program.launches_per_run + 2 + 4  # + init fill/copy + two 2-kernel reductions
         remap = None
         if world > 1:
