@@ -320,6 +320,17 @@ def run_gpu(args):
             "clocks": clocks,
             "result_check": {"p_flag1": last[0], "norm_sq": last[1], "e2e_p_flag1": p_flag},
         }
+        if args.all_configs and world == 1:
+            # BASELINE.json configs[1] and configs[2] on the same box (secondary lines; not the headline)
+            del solver
+            torch.cuda.empty_cache()
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import run_configs
+
+                line["other_configs"] = {"hhl_tridiagonal_n23": run_configs.config2(), "vqls_batch_4096x10q": run_configs.config3()}
+            except Exception as exc:  # never lose the headline line because a secondary config failed
+                line["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -337,6 +348,8 @@ def main():
     ap.add_argument("--cpu-qubits", type=int, default=23, help="size of the bounded CPU sample")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--profile-passes", action="store_true", help="print per-pass timings to stderr")
+    ap.add_argument("--no-all-configs", dest="all_configs", action="store_false",
+                    help="skip the secondary configs (HHL tridiagonal n=23, VQLS batch)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,6 +1,13 @@
 // Dense controlled-e^{iAt} block: selected rows of psi.reshape(-1, 2^nb) are replaced by row @ U^T.
-// v0: shared-memory tiled complex GEMM on the FP64/FP32 vector pipes, out of place into `scratch`,
-// then a copy-back.  (The FP64 tensor-pipe version replaces the inner product; same interface.)
+// Out of place into `scratch`, then a copy-back of the selected rows.
+//   complex128: FP64 tensor pipe.  The complex product is one REAL GEMM
+//       C[M x 2N] = A[M x 2K] * B'[2K x 2N],   B'[2k+c][2n+d] = (Re U[n][k], -Im; Im, Re)
+//   (A = the interleaved (re, im) rows of psi as they lie in HBM, C = interleaved output), issued
+//   as mma.sync.aligned.m8n8k4.f64 (DMMA): 128x64 block tile, 8 warps of 32x32, A tile stored
+//   k-major and both tiles padded by 4 doubles so that every fragment load is bank-conflict free,
+//   register double buffering of the global loads.  (tcgen05.mma has no f64 kind; DMMA is the
+//   FP64 tensor path on sm_100a.)
+//   complex64: shared-memory tiled complex GEMM on the FP32 vector pipe (not a benchmarked path).
 #include "qls_common.cuh"
 
 struct RowSel {
@@ -69,6 +76,103 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- FP64 tensor-pipe version -----------------------------------------------------------------------
+constexpr int DM = 128, DN = 64, DK = 16;  // real-GEMM block tile (M x N' x K'), N' and K' count doubles
+constexpr int LDAT = DM + 4, LDB = DN + 4;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+    qls_ctrl_gemm_dmma_kernel(const double2* __restrict__ psi, double2* __restrict__ out, const double2* __restrict__ U,
+                              int nb, RowSel rs, uint64_t n_rows) {
+  extern __shared__ __align__(16) double dsm[];
+  double (*As)[DK][LDAT] = reinterpret_cast<double (*)[DK][LDAT]>(dsm);                  // [buf][k'][m]
+  double (*Bs)[DK][LDB] = reinterpret_cast<double (*)[DK][LDB]>(dsm + 2 * DK * LDAT);   // [buf][k'][n']
+  const int N = 1 << nb;              // complex columns of psi rows = complex rows/cols of U
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;  // warp tile origin inside the block tile
+  const uint64_t m0 = (uint64_t)blockIdx.y * DM;
+  const int n0c = blockIdx.x * (DN / 2);  // complex column origin
+
+  // global -> register staging: A: 128 rows x 8 complex = 4 per thread; B: 32 complex rows of U x 8 complex = 1 per thread
+  const int a_k = tid & 7;   // complex k within the tile
+  const int a_m = tid >> 3;  // 0..31, rows a_m + 32*j
+  const double2* a_ptr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t m = m0 + a_m + 32 * j;
+    const uint64_t row = gather_segs64(m < n_rows ? m : 0, rs.seg, rs.n_seg) | rs.fix_val;
+    a_ptr[j] = psi + (row << nb) + a_k;
+  }
+  const int b_k = tid & 7, b_n = tid >> 3;  // U[n0c + b_n][k0c + b_k]
+  const double2* b_ptr = U + (size_t)(n0c + b_n) * N + b_k;
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double2 ra[4], rb;
+  auto gload = [&](int kc) {  // kc: complex k origin
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ra[j] = a_ptr[j][kc];
+    rb = b_ptr[kc];
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[buf][2 * a_k][a_m + 32 * j] = ra[j].x;
+      As[buf][2 * a_k + 1][a_m + 32 * j] = ra[j].y;
+    }
+    Bs[buf][2 * b_k][2 * b_n] = rb.x;
+    Bs[buf][2 * b_k + 1][2 * b_n] = -rb.y;
+    Bs[buf][2 * b_k][2 * b_n + 1] = rb.y;
+    Bs[buf][2 * b_k + 1][2 * b_n + 1] = rb.x;
+  };
+
+  const int ktiles = N / (DK / 2);
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < ktiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ktiles) gload((kt + 1) * (DK / 2));
+#pragma unroll
+    for (int k4 = 0; k4 < DK; k4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = As[buf][k4 + t][wm + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[buf][k4 + t][wn + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    if (kt + 1 < ktiles) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  // C fragment: (row g, real columns 2t, 2t+1) = one complex number
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t m = m0 + wm + 8 * i + g;
+    if (m >= n_rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nc = n0c + (wn + 8 * j) / 2 + t;
+      out[(m << nb) + nc] = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256)
     qls_ctrl_gemm_copyback_kernel(V* __restrict__ psi, const V* __restrict__ out, int nb, RowSel rs, uint64_t n_elems) {
@@ -119,9 +223,12 @@ extern "C" int qls_ctrl_gemm(void* state, void* scratch, int n_local, int dtype,
   uint64_t cb = (n_elems + 255) / 256;
   unsigned cgrid = (unsigned)(cb > 148ull * 16 ? 148 * 16 : cb);
   if (dtype == QLS_C128) {
-    qls_ctrl_gemm_kernel<double2><<<grid, 256, 0, s>>>(reinterpret_cast<const double2*>(state),
-                                                       reinterpret_cast<double2*>(scratch),
-                                                       reinterpret_cast<const double2*>(u_dev), nb, rs, n_rows);
+    dim3 dgrid((2 * N) / DN, (unsigned)((n_rows + DM - 1) / DM));
+    const size_t dsmem = sizeof(double) * 2 * DK * (LDAT + LDB);
+    QLS_CUDA(cudaFuncSetAttribute(qls_ctrl_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+    qls_ctrl_gemm_dmma_kernel<<<dgrid, 256, dsmem, s>>>(reinterpret_cast<const double2*>(state),
+                                                    reinterpret_cast<double2*>(scratch),
+                                                    reinterpret_cast<const double2*>(u_dev), nb, rs, n_rows);
     qls_ctrl_gemm_copyback_kernel<double2><<<cgrid, 256, 0, s>>>(reinterpret_cast<double2*>(state),
                                                                  reinterpret_cast<const double2*>(scratch), nb, rs, n_elems);
   } else {

@@ -85,4 +85,5 @@ class TridiagonalToeplitz(ToyModel):
         n = 2**num_qubits
         a = diag * np.eye(n) + off * (np.eye(n, k=1) + np.eye(n, k=-1))
         b = np.random.default_rng(seed).standard_normal(n)
+        b = b / np.linalg.norm(b)  # unit right-hand side: ToyModel.normalize_model is then a no-op
         super().__init__(f"TridiagonalToeplitz(n={num_qubits})", a, b, self.classically_solve(a, b))
