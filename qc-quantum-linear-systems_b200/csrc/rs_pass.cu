@@ -48,14 +48,17 @@ __device__ __forceinline__ uint32_t rs_addr(uint32_t base, const uint32_t (&c)[K
 
 constexpr uint32_t QLS_RS_FLAG_DIRECT = 0x10u;  // STAGE: every register qubit sits above the lane bits
 
-template <typename V, int A, int RQ, bool REAL>
+// CTL = false: the block has no control inside the tile -> straight-line code over all groups, so
+// the scheduler can interleave their independent FMA chains (a per-group predicate turns every
+// group into its own basic block and serialises them).
+template <typename V, int A, int RQ, bool REAL, bool CTL>
 __device__ __forceinline__ void rs_g1(V (&a)[A], const V* __restrict__ M, bool tok, uint32_t rmask, uint32_t rval) {
   const V m00 = __ldg(M), m01 = __ldg(M + 1), m10 = __ldg(M + 2), m11 = __ldg(M + 3);
 #pragma unroll
   for (int p = 0; p < A / 2; ++p) {
     const int i0 = ((p >> RQ) << (RQ + 1)) | (p & ((1 << RQ) - 1));
     const int i1 = i0 | (1 << RQ);
-    if (tok && (((uint32_t)i0 & rmask) == rval)) {
+    if (!CTL || (tok && (((uint32_t)i0 & rmask) == rval))) {
       const V x = a[i0], y = a[i1];
       V b0, b1;
       if (REAL) {
@@ -75,7 +78,7 @@ __device__ __forceinline__ void rs_g1(V (&a)[A], const V* __restrict__ M, bool t
   }
 }
 
-template <typename V, int A, int R1, int R2, bool REAL>
+template <typename V, int A, int R1, int R2, bool REAL, bool CTL>
 __device__ __forceinline__ void rs_g2(V (&a)[A], const V* __restrict__ M, bool tok, uint32_t rmask, uint32_t rval) {
   static_assert(R1 < R2, "register qubits must be ascending");
 #pragma unroll
@@ -83,20 +86,20 @@ __device__ __forceinline__ void rs_g2(V (&a)[A], const V* __restrict__ M, bool t
     const int t0 = ((g >> R1) << (R1 + 1)) | (g & ((1 << R1) - 1));               // zero at R1
     const int i00 = ((t0 >> R2) << (R2 + 1)) | (t0 & ((1 << R2) - 1));            // zero at R2
     const int i01 = i00 | (1 << R1), i10 = i00 | (1 << R2), i11 = i01 | (1 << R2);
-    if (tok && (((uint32_t)i00 & rmask) == rval)) {
+    if (!CTL || (tok && (((uint32_t)i00 & rmask) == rval))) {
       const V x0 = a[i00], x1 = a[i01], x2 = a[i10], x3 = a[i11];
       V o[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
+        const V m0 = __ldg(M + 4 * r), m1 = __ldg(M + 4 * r + 1), m2 = __ldg(M + 4 * r + 2), m3 = __ldg(M + 4 * r + 3);
         if (REAL) {  // H (x) H, CX, RY (x) RY ...: half the multiplies
-          const V m0 = __ldg(M + 4 * r), m1 = __ldg(M + 4 * r + 1), m2 = __ldg(M + 4 * r + 2), m3 = __ldg(M + 4 * r + 3);
           o[r].x = fma(m3.x, x3.x, fma(m2.x, x2.x, fma(m1.x, x1.x, m0.x * x0.x)));
           o[r].y = fma(m3.x, x3.y, fma(m2.x, x2.y, fma(m1.x, x1.y, m0.x * x0.y)));
         } else {
-          o[r] = cmul(__ldg(M + 4 * r), x0);
-          cfma(o[r], __ldg(M + 4 * r + 1), x1);
-          cfma(o[r], __ldg(M + 4 * r + 2), x2);
-          cfma(o[r], __ldg(M + 4 * r + 3), x3);
+          o[r] = cmul(m0, x0);
+          cfma(o[r], m1, x1);
+          cfma(o[r], m2, x2);
+          cfma(o[r], m3, x3);
         }
       }
       a[i00] = o[0];
@@ -158,10 +161,16 @@ template <typename V, int A, int KR>
 __device__ __forceinline__ void rs_dispatch_g1(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
   const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
-#define QLS_G1_CASE(q)                                       \
-  case q:                                                    \
-    if (real) rs_g1<V, A, q, true>(a, M, tok, rm, rv);       \
-    else rs_g1<V, A, q, false>(a, M, tok, rm, rv);           \
+  const bool ctl = (op.ctl_tmask | op.ctl_rmask) != 0;
+#define QLS_G1_CASE(q)                                                   \
+  case q:                                                                \
+    if (ctl) {                                                           \
+      if (real) rs_g1<V, A, q, true, true>(a, M, tok, rm, rv);           \
+      else rs_g1<V, A, q, false, true>(a, M, tok, rm, rv);               \
+    } else {                                                             \
+      if (real) rs_g1<V, A, q, true, false>(a, M, tok, rm, rv);          \
+      else rs_g1<V, A, q, false, false>(a, M, tok, rm, rv);              \
+    }                                                                    \
     break;
   switch (op.r[0]) {
     QLS_G1_CASE(0)
@@ -170,8 +179,8 @@ __device__ __forceinline__ void rs_dispatch_g1(V (&a)[A], const QlsRsOp& op, con
     QLS_G1_CASE(3)
     case 4:
       if constexpr (KR >= 5) {
-        if (real) rs_g1<V, A, 4, true>(a, M, tok, rm, rv);
-        else rs_g1<V, A, 4, false>(a, M, tok, rm, rv);
+        if (real) rs_g1<V, A, 4, true, true>(a, M, tok, rm, rv);
+        else rs_g1<V, A, 4, false, true>(a, M, tok, rm, rv);
       }
       break;
   }
@@ -182,10 +191,17 @@ template <typename V, int A, int KR>
 __device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
   const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
-#define QLS_G2_CASE(p, q)                                   \
-  case (p * 8 + q):                                         \
-    if (real) rs_g2<V, A, p, q, true>(a, M, tok, rm, rv);   \
-    else rs_g2<V, A, p, q, false>(a, M, tok, rm, rv);       \
+  // complex 4x4: keep one basic block per group (the straight-line form interleaves all 64 FMA chains,
+  // runs out of registers and spills -- measured slower); real 4x4 and all 2x2 blocks go straight-line
+  const bool ctl = (op.ctl_tmask | op.ctl_rmask) != 0 || !real;
+#define QLS_G2_CASE(p, q)                                                  \
+  case (p * 8 + q):                                                        \
+    if (ctl) {                                                             \
+      if (real) rs_g2<V, A, p, q, true, true>(a, M, tok, rm, rv);          \
+      else rs_g2<V, A, p, q, false, true>(a, M, tok, rm, rv);              \
+    } else {                                                               \
+      rs_g2<V, A, p, q, true, false>(a, M, tok, rm, rv);                   \
+    }                                                                      \
     break;
   switch (op.r[0] * 8 + op.r[1]) {
     QLS_G2_CASE(0, 1)
@@ -197,10 +213,10 @@ __device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, con
     default:
       if constexpr (KR >= 5) {
         switch (op.r[0]) {
-          case 0: if (real) rs_g2<V, A, 0, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 0, 4, false>(a, M, tok, rm, rv); break;
-          case 1: if (real) rs_g2<V, A, 1, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 1, 4, false>(a, M, tok, rm, rv); break;
-          case 2: if (real) rs_g2<V, A, 2, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 2, 4, false>(a, M, tok, rm, rv); break;
-          case 3: if (real) rs_g2<V, A, 3, 4, true>(a, M, tok, rm, rv); else rs_g2<V, A, 3, 4, false>(a, M, tok, rm, rv); break;
+          case 0: if (real) rs_g2<V, A, 0, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 0, 4, false, true>(a, M, tok, rm, rv); break;
+          case 1: if (real) rs_g2<V, A, 1, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 1, 4, false, true>(a, M, tok, rm, rv); break;
+          case 2: if (real) rs_g2<V, A, 2, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 2, 4, false, true>(a, M, tok, rm, rv); break;
+          case 3: if (real) rs_g2<V, A, 3, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 3, 4, false, true>(a, M, tok, rm, rv); break;
         }
       }
       break;
@@ -241,19 +257,32 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
 
   const int tid = threadIdx.x;
   const int L = rl.L;
+  const int n_rs = rl.n_rs;
 
   // ---- once per CTA ----------------------------------------------------------------------------
-  for (int i = tid; i < rl.n_rs * (int)(sizeof(QlsRsOp) / 16); i += RS_THREADS)
+  // The descriptor arrays of the kernel parameters are copied to shared memory with COMPILE-TIME
+  // indices: a dynamically indexed parameter array makes the compiler spill the whole parameter
+  // struct to local memory, and then even the op-loop bound is a local load on the critical path.
+  __shared__ QlsSeg s_fseg[QLS_MAX_FSEG];
+  __shared__ uint8_t s_high[QLS_MAX_HIGH];
+  if (tid == 0) {
+#pragma unroll
+    for (int j = 0; j < QLS_MAX_FSEG; ++j) s_fseg[j] = rl.fseg[j];
+#pragma unroll
+    for (int j = 0; j < QLS_MAX_HIGH; ++j) s_high[j] = rl.high[j];
+  }
+  for (int i = tid; i < n_rs * (int)(sizeof(QlsRsOp) / 16); i += RS_THREADS)
     reinterpret_cast<uint4*>(sops)[i] = reinterpret_cast<const uint4*>(rs_ops)[i];
+  __syncthreads();
   for (int r = tid; r < (1 << rl.n_high); r += RS_THREADS) {
     uint64_t g = 0;
-    for (int j = 0; j < rl.n_high; ++j) g |= (uint64_t)((r >> j) & 1) << rl.high[j];
+    for (int j = 0; j < rl.n_high; ++j) g |= (uint64_t)((r >> j) & 1) << s_high[j];
     hoff[r] = g;
   }
   __syncthreads();
   {
     int st = 0;
-    for (int o = 0; o < rl.n_rs; ++o) {
+    for (int o = 0; o < n_rs; ++o) {
       if (sops[o].kind == QLS_RS_STAGE) {
         const uint32_t tb = gather_segs32((uint32_t)tid, sops[o].tseg, sops[o].n_tseg);
         ptb[st * RS_THREADS + tid] = (uint16_t)swz<SH>(tb);
@@ -264,22 +293,22 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   __syncthreads();
 
   bool first_direct = false, last_direct = false;
-  if (rl.n_rs > 0) first_direct = (sops[0].flags & QLS_RS_FLAG_DIRECT) != 0;
-  for (int o = 0; o < rl.n_rs; ++o)
+  if (n_rs > 0) first_direct = (sops[0].flags & QLS_RS_FLAG_DIRECT) != 0;
+  for (int o = 0; o < n_rs; ++o)
     if (sops[o].kind == QLS_RS_STAGE) last_direct = (sops[o].flags & QLS_RS_FLAG_DIRECT) != 0;
 
   // ---- persistent loop over tiles ------------------------------------------------------------------
   // The tile counter -> base index deposit walks byte-sized segment descriptors in the kernel
   // parameters; one thread does it per tile and publishes the result (every thread doing it cost
   // more L1 traffic than the tile itself).
-  if (tid == 0) s_base[0] = gather_segs64((uint64_t)blockIdx.x, rl.fseg, rl.n_fseg) | rl.fix_val;
+  if (tid == 0) s_base[0] = gather_segs64((uint64_t)blockIdx.x, s_fseg, rl.n_fseg) | rl.fix_val;
   __syncthreads();
   int parity = 0;
   for (uint64_t tile = blockIdx.x; tile < rl.n_tiles; tile += gridDim.x) {
     const uint64_t base = s_base[parity];
     const uint64_t gbase = base | rl.index_offset;
     if (tid == 0 && tile + gridDim.x < rl.n_tiles)
-      s_base[parity ^ 1] = gather_segs64(tile + gridDim.x, rl.fseg, rl.n_fseg) | rl.fix_val;  // visible after the syncs below
+      s_base[parity ^ 1] = gather_segs64(tile + gridDim.x, s_fseg, rl.n_fseg) | rl.fix_val;  // visible after the syncs below
     parity ^= 1;
 
     if (!first_direct) {
@@ -299,7 +328,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
     uint32_t mytb = 0;
     uint32_t cq[KR];  // swizzled shared-memory offset of each register qubit of the current stage
     uint32_t lq[KR];  // its tile-local bit
-    for (int o = 0; o < rl.n_rs; ++o) {
+    for (int o = 0; o < n_rs; ++o) {
       const QlsRsOp& op = sops[o];
       if (op.kind == QLS_RS_STAGE) {
         if (stage >= 0) {

@@ -33,12 +33,21 @@ __global__ void __launch_bounds__(THREADS, HEAVY ? 2 : 3)
   // combination r, s_base = this tile's base index (tile bits zero, pass-level controls fixed).
   uint64_t* hoff = reinterpret_cast<uint64_t*>(smem_raw + (sizeof(V) << T));
   uint64_t* s_base = hoff + (1 << tl.n_high);
+  __shared__ QlsSeg s_fseg[QLS_MAX_FSEG];  // copied with compile-time indices: keeps `tl` in the constant bank
+  __shared__ uint8_t s_high[QLS_MAX_HIGH];
+  if (tid == 0) {
+#pragma unroll
+    for (int j = 0; j < QLS_MAX_FSEG; ++j) s_fseg[j] = tl.fseg[j];
+#pragma unroll
+    for (int j = 0; j < QLS_MAX_HIGH; ++j) s_high[j] = tl.high[j];
+  }
+  __syncthreads();
   for (int r = tid; r < (1 << tl.n_high); r += THREADS) {
     uint64_t g = 0;
-    for (int j = 0; j < tl.n_high; ++j) g |= (uint64_t)((r >> j) & 1) << tl.high[j];
+    for (int j = 0; j < tl.n_high; ++j) g |= (uint64_t)((r >> j) & 1) << s_high[j];
     hoff[r] = g;
   }
-  if (tid == 0) s_base[0] = gather_segs64((uint64_t)blockIdx.x, tl.fseg, tl.n_fseg) | tl.fix_val;
+  if (tid == 0) s_base[0] = gather_segs64((uint64_t)blockIdx.x, s_fseg, tl.n_fseg) | tl.fix_val;
   __syncthreads();
   const uint64_t base = s_base[0];
 

@@ -332,6 +332,33 @@ def tensor_merge(blocks: Sequence[Block], max_fuse_qubits: int = 3) -> List[Bloc
     return out
 
 
+def split_table_controls(qubits: Sequence[int], table: np.ndarray):
+    """A table qubit whose 0-half (or 1-half) is identically 1 is really a control: e.g. every
+    controlled-phase ladder of the QFT is the identity on the control = 0 half.  Returns the reduced
+    (qubits, table) and ``{qubit: value}`` -- half the lookups and multiplies per extracted qubit."""
+    qubits = list(qubits)
+    tab = np.asarray(table)
+    controls: Dict[int, int] = {}
+    changed = True
+    while changed and qubits:
+        changed = False
+        for j in range(len(qubits)):
+            view = tab.reshape(-1, 2, 2**j)  # [high bits][bit j][low bits]
+            zero_half, one_half = view[:, 0, :], view[:, 1, :]
+            if np.all(zero_half == 1):
+                controls[qubits[j]] = 1
+                tab = one_half.reshape(-1)
+            elif np.all(one_half == 1):
+                controls[qubits[j]] = 0
+                tab = zero_half.reshape(-1)
+            else:
+                continue
+            del qubits[j]
+            changed = True
+            break
+    return qubits, tab, controls
+
+
 def _mux_expand(angles: np.ndarray, sel: Sequence[int], union: Sequence[int]) -> np.ndarray:
     """Angle table over ``union`` (bit j = union[j]) of a table over ``sel``."""
     idx = np.arange(2 ** len(union))
@@ -799,8 +826,10 @@ class _Emitter:
                     tab *= ft[sub]
                 op = _abi.QlsRsOp()
                 op.kind = _abi.QLS_RS_DIAG
-                self._rs_table_fields(op, qs, local_pos, rho, tbit)
-                op.pool_off = self._pool_add(tab)
+                qs2, tab2, ctl = split_table_controls(qs, tab)
+                self._rs_table_fields(op, qs2, local_pos, rho, tbit)
+                self._rs_controls(op, ctl, local_pos, rho, tbit)
+                op.pool_off = self._pool_add(tab2)
                 yield op
         else:
             raise _RsUnsupported(b.kind)

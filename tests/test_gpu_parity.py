@@ -376,3 +376,41 @@ def test_register_stage_kernel_hhl_shaped_many_tiles(cuda_device):
     got = Statevector(qc).data
     assert np.max(np.abs(got - want)) <= TOL64
     assert _fidelity(got, want) >= FID
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+
+
+def test_edge_case_circuits_on_gpu(cuda_device):
+    from qls_b200.statevector import Statevector
+
+    from test_lowering import _edge_circuits
+
+    for name, qc in _edge_circuits().items():
+        want = numpy_sv.run(qc.num_qubits, circuit_to_stream(qc))
+        for fused in (True, False):
+            got = Statevector(qc, fused=fused).data
+            assert np.max(np.abs(got - want)) <= 1e-14, (name, fused)
+        got32 = Statevector(qc, precision="fp32").data
+        assert np.max(np.abs(got32 - want)) <= TOL32, name
+
+
+def test_unbound_parameters_are_rejected(cuda_device):
+    from qls_b200.library import RealAmplitudes
+    from qls_b200.statevector import Statevector
+
+    with pytest.raises(ValueError):
+        Statevector(RealAmplitudes(2, reps=1))
+
+
+def test_library_error_codes_surface_as_exceptions(cuda_device):
+    import ctypes as C
+
+    from qls_b200 import _abi
+
+    lib = _abi.load()
+    with pytest.raises(_abi.QlsError):
+        _abi.check(lib.qls_sv_init_basis(None, 4, 0, 0, None))
+    out = (C.c_double * 2)()
+    with pytest.raises(_abi.QlsError):
+        _abi.check(lib.qls_reduce(None, 4, 0, 0, 0, 0, 0, None, None, out, None))

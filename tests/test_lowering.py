@@ -167,3 +167,60 @@ def test_wide_dense_blocks_keep_the_sweep_form():
     qc.unitary(random_unitary(3, rng), [1, 5, 12])
     low = lower_circuit(qc, LoweringOptions())
     assert all(p.rs_stages == 0 for p in low.pass_info)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+
+
+def _edge_circuits():
+    from qls_b200.circuit import Gate
+    out = {}
+    qc = QuantumCircuit(3, name="empty")
+    out["empty"] = qc
+    qc = QuantumCircuit(1, name="one_qubit")
+    qc.h(0)
+    qc.t(0)
+    qc.h(0)
+    out["one_qubit"] = qc
+    qc = QuantumCircuit(4, name="diag_only", global_phase=0.3)
+    for q in range(4):
+        qc.rz(0.1 * (q + 1), q)
+    qc.cp(0.7, 0, 3)
+    qc.cz(1, 2)
+    out["diag_only"] = qc
+    qc = QuantumCircuit(4, name="cancelling")
+    for q in range(4):
+        qc.h(q)
+        qc.h(q)
+    qc.cx(0, 1)
+    qc.cx(0, 1)
+    out["cancelling"] = qc
+    qc = QuantumCircuit(2, name="phase_only", global_phase=1.234)
+    out["phase_only"] = qc
+    qc = QuantumCircuit(5, name="negative_controls")
+    for q in range(5):
+        qc.h(q)
+    qc.append(Gate("x", 1).control(2, ctrl_state=0b01), [0, 3, 4])
+    qc.append(Gate("ry", 1, [0.9]).control(1, ctrl_state=0), [2, 1])
+    out["negative_controls"] = qc
+    qc = QuantumCircuit(6, name="prep_then_gates")
+    amps = np.arange(1, 9, dtype=complex)
+    amps[3] *= 1j
+    amps /= np.linalg.norm(amps)
+    qc.prepare_state(amps, [0, 1, 2])
+    qc.h(4)
+    qc.cx(4, 0)
+    out["prep_then_gates"] = qc
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_edge_circuits()))
+def test_edge_case_circuits(name):
+    qc = _edge_circuits()[name]
+    n = qc.num_qubits
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    for fused in (True, False):
+        low = lower_circuit(qc, LoweringOptions(tile_bits=3, max_high=1), fused=fused)
+        got = run_program(low)
+        assert np.max(np.abs(got - want)) < 1e-14, (name, fused)
+    assert abs(np.linalg.norm(want) - 1) < 1e-14
