@@ -39,12 +39,17 @@ struct QlsProgram {
   uint32_t n_rs_ops;
   unsigned char* pool_dev;
   uint64_t pool_bytes;
+  // register-stage form: per-pass constant-memory images (header + micro-ops + matrices), device resident
+  unsigned char* rs_img_dev;
+  uint64_t* rs_img_off;    // [n_passes] byte offset into rs_img_dev
+  uint32_t* rs_img_bytes;  // [n_passes] 0: the pass has no register-stage form
 };
 
 // register-stage fast path (rs_pass.cu)
-bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, int n_local);
-int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset,
-                       cudaStream_t stream);
+int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsigned char* pool_host);
+bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, int n_local);
+int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
+                       uint64_t index_offset, cudaStream_t stream);
 
 // ---- complex arithmetic on double2 / float2 -----------------------------------------------------
 template <typename R>

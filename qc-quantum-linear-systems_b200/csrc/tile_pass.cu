@@ -138,8 +138,8 @@ extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local,
     int rc = validate_pass(p, n_local, prog->dtype);
     if (rc) return rc;
     QLS_ARG(!(p.pad & 4u), "pass %u holds batch-only ops (PARAM / MATVEC): use qls_batch_expect_z", i);
-    if (!g_sweep_only && qls_rs_eligible(prog, p, n_local)) {
-      rc = qls_launch_rs_pass(prog, p, state, n_local, index_offset, s);
+    if (!g_sweep_only && qls_rs_eligible(prog, p, i, n_local)) {
+      rc = qls_launch_rs_pass(prog, p, i, state, n_local, index_offset, s);
       if (rc) return rc;
       continue;
     }
@@ -200,6 +200,9 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   p->passes_host = new QlsPass[n_passes ? n_passes : 1];
   p->ops_dev = nullptr;
   p->pool_dev = nullptr;
+  p->rs_img_dev = nullptr;
+  p->rs_img_off = nullptr;
+  p->rs_img_bytes = nullptr;
   for (uint32_t i = 0; i < n_passes; ++i) {
     p->passes_host[i] = passes_host[i];
     QlsPass& ps = p->passes_host[i];
@@ -249,8 +252,13 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
     e = cudaMalloc(&p->pool_dev, pool_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(p->pool_dev, pool_host, pool_bytes, cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess && qls_rs_build_images(p, rs_ops_host, static_cast<const unsigned char*>(pool_host)) != QLS_OK)
+    e = cudaErrorUnknown;
   if (e != cudaSuccess) {
-    qls_set_error("qls_program_create: %s", cudaGetErrorString(e));
+    if (e != cudaErrorUnknown) qls_set_error("qls_program_create: %s", cudaGetErrorString(e));
+    if (p->rs_img_dev) cudaFree(p->rs_img_dev);
+    delete[] p->rs_img_off;
+    delete[] p->rs_img_bytes;
     if (p->ops_dev) cudaFree(p->ops_dev);
     if (p->rs_ops_dev) cudaFree(p->rs_ops_dev);
     if (p->pool_dev) cudaFree(p->pool_dev);
@@ -268,6 +276,9 @@ extern "C" int qls_program_destroy(QlsProgram* prog) {
   if (prog->ops_dev) cudaFree(prog->ops_dev);
   if (prog->rs_ops_dev) cudaFree(prog->rs_ops_dev);
   if (prog->pool_dev) cudaFree(prog->pool_dev);
+  if (prog->rs_img_dev) cudaFree(prog->rs_img_dev);
+  delete[] prog->rs_img_off;
+  delete[] prog->rs_img_bytes;
   delete[] prog->passes_host;
   delete prog;
   return QLS_OK;
