@@ -43,6 +43,7 @@ struct QlsProgram {
   unsigned char* rs_img_dev;
   uint64_t* rs_img_off;    // [n_passes] byte offset into rs_img_dev
   uint32_t* rs_img_bytes;  // [n_passes] 0: the pass has no register-stage form
+  uint8_t* rs_img_kr;      // [n_passes] register qubits per thread of the pass's stages (4 or 5)
 };
 
 // register-stage fast path (rs_pass.cu)

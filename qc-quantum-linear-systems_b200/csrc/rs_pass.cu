@@ -19,6 +19,7 @@
 //   * the next tile of the CTA is prefetched into L2 (cp.async.bulk.prefetch) while the current
 //     one is in registers, so the HBM read latency is off the critical path;
 //   * diagonal tables / multiplexer angles are fetched in batches before they are used.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -27,28 +28,61 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
 constexpr int RS_MAX_OPS = 160;
+#ifndef RS_CTAS_F64_KR5
+#define RS_CTAS_F64_KR5 2
+#endif
 constexpr int RS_MAX_STAGES = 24;
-constexpr int RS_MAX_XC = 8;
+constexpr int RS_MAX_CBITS = 6;
 constexpr int RS_IMG_BYTES = 60 * 1024;
 constexpr uint32_t QLS_RS_FLAG_DIRECT = 0x10u;  // STAGE: every register qubit sits above the lane bits
+constexpr uint32_t QLS_RS_FLAG_KR5 = 0x20u;     // STAGE: five register qubits (r[0..3], pad0), 2^(T-5) threads
 
 struct RsHeader {  // 256 bytes
-  int32_t L, n_high, n_fseg, n_ops;
+  int32_t L, n_high, n_fseg, n_recs;
   uint64_t fix_val;
-  int32_t n_xc;  // distinct (mask, value) pairs of controls outside the tile; 0: some op always fires
+  int32_t n_cbits;     // control qubits outside the tile whose values select the step list (variant)
   int32_t n_stages;
-  uint64_t xc_mask[RS_MAX_XC], xc_val[RS_MAX_XC];
+  uint32_t steps_off;  // byte offset of RsStep[] in the image body
+  uint32_t pad0;
+  uint8_t cbit[8];     // their global index bit positions
   uint8_t high[QLS_MAX_HIGH];
   QlsSeg fseg[QLS_MAX_FSEG];
-  uint8_t pad[24];
+  uint16_t vstart[1 << RS_MAX_CBITS];  // first step of each variant; RS_IDLE: no op fires, tile untouched
+  uint8_t pad[8];
 };
 static_assert(sizeof(RsHeader) == 256, "RsHeader layout");
 
+// One step of a variant's straight-line program (8 bytes, constant memory).
+struct RsStep {
+  uint16_t code;  // RS_C_*
+  uint16_t rec;   // index of the QlsRsOp record (op fields / the stage entered)
+  uint16_t aux;   // TRANS: record index of the stage being left
+  uint16_t moff;  // G1/G2: matrix offset in the image body, in 16-byte units
+};
+
+enum {
+  RS_C_LOAD_D = 1,   // global -> registers (lanes are the low tile bits)
+  RS_C_LOAD_S = 2,   // global -> shared (cp.async) -> registers
+  RS_C_TRANS = 3,    // registers -> shared -> registers in the next stage's layout
+  RS_C_STORE_D = 4,  // registers -> global; ends the tile
+  RS_C_STORE_S = 5,  // registers -> shared -> global; ends the tile
+  RS_C_DIAG = 6,     // table indexed by register qubits and/or controlled inside the tile
+  RS_C_DIAG1 = 7,    // one phase per thread
+  RS_C_MUX = 8,      // + register qubit
+  RS_C_G1 = 16,      // + 4 * register qubit + 2 * real + ctl
+  RS_C_G2 = 64       // + 4 * pair + 2 * real + ctl
+};
+constexpr uint16_t RS_IDLE = 0xFFFFu;
+
+// pair index of register qubits p < q: the six pairs below 4 first (KR = 4), then (p, 4)
+__host__ __device__ constexpr int rs_pair(int p, int q) { return q == 4 ? 6 + p : (p == 0 ? q - 1 : p + q); }
+static_assert(rs_pair(0, 1) == 0 && rs_pair(0, 2) == 1 && rs_pair(0, 3) == 2 && rs_pair(1, 2) == 3 && rs_pair(1, 3) == 4 &&
+                  rs_pair(2, 3) == 5 && rs_pair(0, 4) == 6 && rs_pair(3, 4) == 9, "pair numbering");
+
 struct RsImage {
   RsHeader h;
-  unsigned char body[RS_IMG_BYTES - sizeof(RsHeader)];  // QlsRsOp[n_ops], then the gate matrices
+  unsigned char body[RS_IMG_BYTES - sizeof(RsHeader)];  // QlsRsOp[n_recs], gate matrices, RsStep[]
 };
 
 __constant__ RsImage c_img;
@@ -152,24 +186,24 @@ __device__ __forceinline__ uint32_t rs_tidx(uint32_t base, const uint32_t (&d)[K
   return t;
 }
 
+// one phase per thread: the table looks at no register qubit and there is no register-bit control
+template <typename V, int A>
+__device__ __forceinline__ void rs_diag1(V (&a)[A], const V* __restrict__ table, uint32_t ti0, bool tok) {
+  V ph = __ldg(&table[ti0]);
+  if (!tok) {
+    ph.x = 1;
+    ph.y = 0;
+  }
+#pragma unroll
+  for (int r = 0; r < A; ++r) a[r] = cmul(a[r], ph);
+}
+
 template <typename V, int A, int KR>
 __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
   uint32_t d[KR];
-  uint32_t any = 0;
 #pragma unroll
-  for (int j = 0; j < KR; ++j) {
-    d[j] = op.rt[1 << j];
-    any |= d[j];
-  }
+  for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
-  if ((any | rm) == 0) {  // warp-uniform: the table does not look at a register qubit -> one phase per thread
-    const V ph = __ldg(&table[ti0]);
-    if (tok) {
-#pragma unroll
-      for (int r = 0; r < A; ++r) a[r] = cmul(a[r], ph);
-    }
-    return;
-  }
   constexpr int CH = 4;  // phases fetched per batch (register budget)
 #pragma unroll
   for (int c = 0; c < A; c += CH) {
@@ -217,85 +251,6 @@ __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* 
   }
 }
 
-template <typename V, int A, int KR>
-__device__ __forceinline__ void rs_dispatch_g1(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
-  const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
-  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
-  const bool ctl = (op.ctl_tmask | op.ctl_rmask) != 0;
-#define QLS_G1_CASE(q)                                                   \
-  case q:                                                                \
-    if (ctl) {                                                           \
-      if (real) rs_g1<V, A, q, true, true>(a, M, tok, rm, rv);           \
-      else rs_g1<V, A, q, false, true>(a, M, tok, rm, rv);               \
-    } else {                                                             \
-      if (real) rs_g1<V, A, q, true, false>(a, M, tok, rm, rv);          \
-      else rs_g1<V, A, q, false, false>(a, M, tok, rm, rv);              \
-    }                                                                    \
-    break;
-  switch (op.r[0]) {
-    QLS_G1_CASE(0)
-    QLS_G1_CASE(1)
-    QLS_G1_CASE(2)
-    QLS_G1_CASE(3)
-    case 4:
-      if constexpr (KR >= 5) {
-        if (real) rs_g1<V, A, 4, true, true>(a, M, tok, rm, rv);
-        else rs_g1<V, A, 4, false, true>(a, M, tok, rm, rv);
-      }
-      break;
-  }
-#undef QLS_G1_CASE
-}
-
-template <typename V, int A, int KR>
-__device__ __forceinline__ void rs_dispatch_g2(V (&a)[A], const QlsRsOp& op, const V* M, bool tok) {
-  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
-  const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
-  const bool ctl = (op.ctl_tmask | op.ctl_rmask) != 0;
-#define QLS_G2_CASE(p, q)                                                  \
-  case (p * 8 + q):                                                        \
-    if (ctl) {                                                             \
-      if (real) rs_g2<V, A, p, q, true, true>(a, M, tok, rm, rv);          \
-      else rs_g2<V, A, p, q, false, true>(a, M, tok, rm, rv);              \
-    } else {                                                               \
-      if (real) rs_g2<V, A, p, q, true, false>(a, M, tok, rm, rv);         \
-      else rs_g2<V, A, p, q, false, false>(a, M, tok, rm, rv);             \
-    }                                                                      \
-    break;
-  switch (op.r[0] * 8 + op.r[1]) {
-    QLS_G2_CASE(0, 1)
-    QLS_G2_CASE(0, 2)
-    QLS_G2_CASE(0, 3)
-    QLS_G2_CASE(1, 2)
-    QLS_G2_CASE(1, 3)
-    QLS_G2_CASE(2, 3)
-    default:
-      if constexpr (KR >= 5) {
-        switch (op.r[0]) {
-          case 0: if (real) rs_g2<V, A, 0, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 0, 4, false, true>(a, M, tok, rm, rv); break;
-          case 1: if (real) rs_g2<V, A, 1, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 1, 4, false, true>(a, M, tok, rm, rv); break;
-          case 2: if (real) rs_g2<V, A, 2, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 2, 4, false, true>(a, M, tok, rm, rv); break;
-          case 3: if (real) rs_g2<V, A, 3, 4, true, true>(a, M, tok, rm, rv); else rs_g2<V, A, 3, 4, false, true>(a, M, tok, rm, rv); break;
-        }
-      }
-      break;
-  }
-#undef QLS_G2_CASE
-}
-
-template <typename V, int A, int KR>
-__device__ __forceinline__ void rs_dispatch_muxry(V (&a)[A], const QlsRsOp& op, const V* table, uint32_t ti0, bool tok) {
-  switch (op.r[0]) {
-    case 0: rs_muxry<V, A, KR, 0>(a, op, table, ti0, tok); break;
-    case 1: rs_muxry<V, A, KR, 1>(a, op, table, ti0, tok); break;
-    case 2: rs_muxry<V, A, KR, 2>(a, op, table, ti0, tok); break;
-    case 3: rs_muxry<V, A, KR, 3>(a, op, table, ti0, tok); break;
-    case 4:
-      if constexpr (KR >= 5) rs_muxry<V, A, KR, 4>(a, op, table, ti0, tok);
-      break;
-  }
-}
-
 template <int KR, int SH>
 __device__ __forceinline__ void rs_stage_bits(const QlsRsOp& sp, uint32_t (&cq)[KR], uint32_t (&lq)[KR]) {
 #pragma unroll
@@ -305,28 +260,26 @@ __device__ __forceinline__ void rs_stage_bits(const QlsRsOp& sp, uint32_t (&cq)[
   }
 }
 
-// A warp vote makes a condition PROVABLY warp-uniform for ptxas.  Every branch that guards a barrier
-// goes through it: with a condition ptxas cannot prove uniform (loop-carried state such as the current
-// stage) it gives up on the uniform datapath for the whole tile loop -- the op records and gate
-// matrices then come through per-thread LDC + vector registers instead of LDCU + uniform-register
-// DFMA operands, and the kernel spills.
-__device__ __forceinline__ bool uni(bool c) { return __any_sync(0xffffffffu, c) != 0; }
-
-// true if no op of the pass fires on the tile whose global base index is gbase (warp-uniform)
-__device__ __forceinline__ bool rs_tile_idle(uint64_t gbase) {
-  const int n = c_img.h.n_xc;
-  if (n == 0) return false;
-  bool hit = false;
-  for (int j = 0; j < n; ++j) hit |= (gbase & c_img.h.xc_mask[j]) == c_img.h.xc_val[j];
-  return !hit;
+// variant of the tile whose global base index is gbase: the values of the pass's control qubits
+__device__ __forceinline__ uint32_t rs_variant(uint64_t gbase) {
+  uint32_t v = 0;
+  const int n = c_img.h.n_cbits;
+  for (int j = 0; j < n; ++j) v |= (uint32_t)((gbase >> c_img.h.cbit[j]) & 1ull) << j;
+  return v;
 }
 
-template <typename R, int T, int KR>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+// The per-tile program is a straight list of RsStep records chosen by the tile's control-qubit
+// values (built on the host, qls_rs_build_images): no control test, no stage bookkeeping and no
+// loop-carried state besides the step counter is left in the kernel.  ptxas keeps the whole step
+// loop on the uniform datapath only if it can PROVE every branch around a barrier warp-uniform; a
+// warp shuffle of the step counter makes that proof trivial (loop-carried state it cannot see
+// through makes it fall back to per-thread LDC + vector-register operands, and the kernel spills).
+template <typename R, int T, int KR, int CTAS>
+__global__ void __launch_bounds__(1 << (T - KR), CTAS)
     qls_rs_pass_kernel(typename Vec2<R>::type* __restrict__ state, const uint64_t index_offset, const uint64_t n_tiles,
-                       const unsigned char* __restrict__ pool) {
+                       const unsigned char* __restrict__ pool, const uint32_t dbg) {
   using V = typename Vec2<R>::type;
-  static_assert((1 << (T - KR)) == RS_THREADS, "the threads index the non-register tile bits");
+  constexpr int RS_THREADS = 1 << (T - KR);  // the threads index the non-register tile bits
   constexpr int A = 1 << KR;
   constexpr int SH = sizeof(V) == 16 ? 0 : 1;
   constexpr int APU = 1 << SH;           // amplitudes per 16-byte unit
@@ -338,10 +291,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   uint64_t* hoff = reinterpret_cast<uint64_t*>(smem_raw + TILE_BYTES);  // [1 << n_high]
   uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << c_img.h.n_high));  // [stages][RS_THREADS]
 
-  const QlsRsOp* __restrict__ ops = reinterpret_cast<const QlsRsOp*>(c_img.body);
+  const QlsRsOp* recs = reinterpret_cast<const QlsRsOp*>(c_img.body);
   const int tid = threadIdx.x;
   const int L = c_img.h.L;
-  const int n_ops = c_img.h.n_ops;
+  const int n_recs = c_img.h.n_recs;
   const int n_high = c_img.h.n_high;
   const int n_fseg = c_img.h.n_fseg;
 
@@ -351,14 +304,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
     for (int j = 0; j < n_high; ++j) g |= (uint64_t)((r >> j) & 1) << c_img.h.high[j];
     hoff[r] = g;
   }
-  {
-    int st = 0;
-    for (int o = 0; o < n_ops; ++o) {
-      if (ops[o].kind == QLS_RS_STAGE) {
-        const uint32_t tb = gather_segs32((uint32_t)tid, ops[o].tseg, ops[o].n_tseg);
-        ptb[st * RS_THREADS + tid] = (uint16_t)swz<SH>(tb);
-        ++st;
-      }
+  for (int o = 0; o < n_recs; ++o) {
+    if (recs[o].kind == QLS_RS_STAGE) {
+      const uint32_t tb = gather_segs32((uint32_t)tid, recs[o].tseg, recs[o].n_tseg);
+      ptb[(uint32_t)recs[o].pool_off * RS_THREADS + tid] = (uint16_t)swz<SH>(tb);  // pool_off of a STAGE = its ordinal
     }
   }
   // L2 prefetch geometry: the tile is 2^n_high runs of 2^L amplitudes; units of <= 4 KB
@@ -376,7 +325,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
       const uint64_t nt = tile + gridDim.x;
       if (nt < n_tiles) {
         const uint64_t nbase = gather_segs64(nt, c_img.h.fseg, n_fseg) | c_img.h.fix_val;
-        if (!rs_tile_idle(nbase | index_offset)) {
+        if (c_img.h.vstart[rs_variant(nbase | index_offset)] != RS_IDLE) {
           for (uint32_t u = tid; u < pf_units; u += RS_THREADS) {
             const uint64_t g = nbase | hoff[u >> pf_per_run_log];
             prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(&state[g]) + (size_t)(u & ((1u << pf_per_run_log) - 1u)) * pf_bytes,
@@ -385,34 +334,37 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
         }
       }
     }
-    if (uni(rs_tile_idle(gbase))) continue;  // warp- and block-uniform
+    uint32_t s = __shfl_sync(0xffffffffu, (uint32_t)c_img.h.vstart[rs_variant(gbase)], 0);
+    if (s == RS_IDLE) continue;  // no op fires on this tile: neither read nor written
+    const RsStep* steps = reinterpret_cast<const RsStep*>(c_img.body + c_img.h.steps_off);
 
     V a[A];
-    int cur = -1;        // op index of the STAGE whose layout the registers are in (-1: tile not loaded yet)
-    int pend = -1;       // latest STAGE record seen
-    int pend_ord = -1;   // its ordinal (row of ptb)
-    bool cur_direct = false;
-    uint32_t mytb = 0;
-    for (int o = 0; o < n_ops; ++o) {
-      const QlsRsOp& op = ops[o];
-      if (uni(op.kind == QLS_RS_STAGE)) {
-        pend = o;
-        ++pend_ord;
-        continue;
-      }
-      if (uni((gbase & op.xc_mask) != op.xc_val)) continue;  // block-uniform
-      if (uni(pend != cur)) {
-        // ---- enter the pending stage (barriers are unconditional inside this block) ----
-        const QlsRsOp& sp = ops[pend];
-        const bool was_loaded = cur >= 0;
-        const bool new_direct = (sp.flags & QLS_RS_FLAG_DIRECT) != 0;
-        __syncthreads();  // every thread is done with the previous shared-memory image
-        if (was_loaded) {
+    for (;;) {
+      s = __shfl_sync(0xffffffffu, s, 0);  // provably warp-uniform step counter (see above)
+      const RsStep st = steps[s];
+      ++s;
+      const QlsRsOp& op = recs[st.rec];
+      const V* M = reinterpret_cast<const V*>(c_img.body + 16u * st.moff);
+      const bool skip = KR == 4 && sizeof(V) == 16 && dbg != 0 && (((dbg & 1u) && st.code >= RS_C_G1) || ((dbg & 2u) && st.code == RS_C_TRANS) ||
+                                    ((dbg & 4u) && st.code >= RS_C_DIAG && st.code < RS_C_G1));  // timing experiments only
+      if (!__any_sync(0xffffffffu, skip)) switch (st.code) {
+        case RS_C_LOAD_D: {
+          // all register qubits sit above the 5 lane bits: every warp load is 512 contiguous bytes
           uint32_t cq[KR], lq[KR];
-          rs_stage_bits<KR, SH>(ops[cur], cq, lq);
+          rs_stage_bits<KR, SH>(op, cq, lq);
+          const uint32_t ltb = swz<SH>(ptb[(uint32_t)op.pool_off * RS_THREADS + tid]);  // the swizzle is an involution
 #pragma unroll
-          for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
-        } else if (!new_direct) {
+          for (int r = 0; r < A; ++r) {
+            const uint32_t idx = rs_addr<KR>(ltb, lq, r);
+            a[r] = state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]];
+          }
+          break;
+        }
+        case RS_C_LOAD_S: {
+          uint32_t cq[KR], lq[KR];
+          rs_stage_bits<KR, SH>(op, cq, lq);
+          const uint32_t mytb = ptb[(uint32_t)op.pool_off * RS_THREADS + tid];
+          __syncthreads();  // the previous tile's write-back has left shared memory
 #pragma unroll 4
           for (int u = tid; u < UNITS; u += RS_THREADS) {
             const int i = u * APU;
@@ -421,98 +373,150 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
           }
           cp_async_commit();
           cp_async_wait<0>();
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
+          break;
         }
-        mytb = ptb[pend_ord * RS_THREADS + tid];
-        uint32_t cq[KR], lq[KR];  // swizzled shared-memory offset / tile-local bit of each register qubit
-        rs_stage_bits<KR, SH>(sp, cq, lq);
-        __syncthreads();
-        if (!was_loaded && new_direct) {
-          // all register qubits sit above the 5 lane bits: every warp load is 512 contiguous bytes
-          const uint32_t ltb = swz<SH>(mytb);  // the swizzle is an involution
+        case RS_C_TRANS: {
+          const QlsRsOp& from = recs[st.aux];
+          uint32_t cq[KR], lq[KR];
+          rs_stage_bits<KR, SH>(from, cq, lq);
+          uint32_t mytb = ptb[(uint32_t)from.pool_off * RS_THREADS + tid];
+          __syncthreads();  // every thread is done with the previous shared-memory image
+#pragma unroll
+          for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
+          rs_stage_bits<KR, SH>(op, cq, lq);
+          mytb = ptb[(uint32_t)op.pool_off * RS_THREADS + tid];
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
+          break;
+        }
+        case RS_C_STORE_D: {
+          uint32_t cq[KR], lq[KR];
+          rs_stage_bits<KR, SH>(op, cq, lq);
+          const uint32_t ltb = swz<SH>(ptb[(uint32_t)op.pool_off * RS_THREADS + tid]);
 #pragma unroll
           for (int r = 0; r < A; ++r) {
             const uint32_t idx = rs_addr<KR>(ltb, lq, r);
-            a[r] = state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]];
+            state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]] = a[r];
           }
-        } else {
-#pragma unroll
-          for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
-        }
-        cur_direct = new_direct;
-        cur = pend;
-      }
-      const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;
-      switch (op.kind) {
-        case QLS_RS_G1:
-          rs_dispatch_g1<V, A, KR>(a, op, reinterpret_cast<const V*>(c_img.body + op.pool_off), tok);
-          break;
-        case QLS_RS_G2:
-          rs_dispatch_g2<V, A, KR>(a, op, reinterpret_cast<const V*>(c_img.body + op.pool_off), tok);
-          break;
-        case QLS_RS_DIAG: {
-          const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
-          rs_diag<V, A, KR>(a, op, reinterpret_cast<const V*>(pool + op.pool_off), ti0, tok);
           break;
         }
-        case QLS_RS_MUXRY: {
-          const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
-          rs_dispatch_muxry<V, A, KR>(a, op, reinterpret_cast<const V*>(pool + op.pool_off), ti0, tok);
-          break;
-        }
-      }
-    }
-    if (uni(cur < 0)) continue;  // nothing fired (possible only when tile skipping is off): tile untouched
-    uint32_t cq[KR], lq[KR];
-    rs_stage_bits<KR, SH>(ops[cur], cq, lq);
-    __syncthreads();
-    if (!cur_direct) {
+        case RS_C_STORE_S: {
+          uint32_t cq[KR], lq[KR];
+          rs_stage_bits<KR, SH>(op, cq, lq);
+          const uint32_t mytb = ptb[(uint32_t)op.pool_off * RS_THREADS + tid];
+          __syncthreads();
 #pragma unroll
-      for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
-    }
-    __syncthreads();
-    if (cur_direct) {
-      const uint32_t ltb = swz<SH>(mytb);
-#pragma unroll
-      for (int r = 0; r < A; ++r) {
-        const uint32_t idx = rs_addr<KR>(ltb, lq, r);
-        state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]] = a[r];
-      }
-    } else {
+          for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
+          __syncthreads();
 #pragma unroll 4
-      for (int u = tid; u < UNITS; u += RS_THREADS) {
-        const int i = u * APU;
-        const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
-        *reinterpret_cast<uint4*>(&state[g]) = sm16[swz<SH>((uint32_t)i) >> SH];
+          for (int u = tid; u < UNITS; u += RS_THREADS) {
+            const int i = u * APU;
+            const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
+            *reinterpret_cast<uint4*>(&state[g]) = sm16[swz<SH>((uint32_t)i) >> SH];
+          }
+          break;
+        }
+        case RS_C_DIAG:
+        case RS_C_DIAG1: {
+          const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;
+          const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
+          const V* table = reinterpret_cast<const V*>(pool + op.pool_off);
+          if (st.code == RS_C_DIAG1) rs_diag1<V, A>(a, table, ti0, tok);
+          else rs_diag<V, A, KR>(a, op, table, ti0, tok);
+          break;
+        }
+#define QLS_MUX_CASE(q)                                                                                              \
+  case RS_C_MUX + q: {                                                                                               \
+    const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;                                                  \
+    const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg); \
+    rs_muxry<V, A, KR, q>(a, op, reinterpret_cast<const V*>(pool + op.pool_off), ti0, tok);                          \
+    break;                                                                                                           \
+  }
+        QLS_MUX_CASE(0)
+        QLS_MUX_CASE(1)
+        QLS_MUX_CASE(2)
+        QLS_MUX_CASE(3)
+#define QLS_G1_CASE(q)                                                                                               \
+  case RS_C_G1 + 4 * q + 0: rs_g1<V, A, q, false, false>(a, M, true, 0, 0); break;                                   \
+  case RS_C_G1 + 4 * q + 2: rs_g1<V, A, q, true, false>(a, M, true, 0, 0); break;                                    \
+  case RS_C_G1 + 4 * q + 1:                                                                                          \
+    rs_g1<V, A, q, false, true>(a, M, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval, op.ctl_rmask, op.ctl_rval);      \
+    break;                                                                                                           \
+  case RS_C_G1 + 4 * q + 3:                                                                                          \
+    rs_g1<V, A, q, true, true>(a, M, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval, op.ctl_rmask, op.ctl_rval);       \
+    break;
+        QLS_G1_CASE(0)
+        QLS_G1_CASE(1)
+        QLS_G1_CASE(2)
+        QLS_G1_CASE(3)
+#define QLS_G2_CASE(p, q)                                                                                            \
+  case RS_C_G2 + 4 * rs_pair(p, q) + 0: rs_g2<V, A, p, q, false, false>(a, M, true, 0, 0); break;                    \
+  case RS_C_G2 + 4 * rs_pair(p, q) + 2: rs_g2<V, A, p, q, true, false>(a, M, true, 0, 0); break;                     \
+  case RS_C_G2 + 4 * rs_pair(p, q) + 1:                                                                              \
+    rs_g2<V, A, p, q, false, true>(a, M, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval, op.ctl_rmask, op.ctl_rval);   \
+    break;                                                                                                           \
+  case RS_C_G2 + 4 * rs_pair(p, q) + 3:                                                                              \
+    rs_g2<V, A, p, q, true, true>(a, M, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval, op.ctl_rmask, op.ctl_rval);    \
+    break;
+        QLS_G2_CASE(0, 1)
+        QLS_G2_CASE(0, 2)
+        QLS_G2_CASE(0, 3)
+        QLS_G2_CASE(1, 2)
+        QLS_G2_CASE(1, 3)
+        QLS_G2_CASE(2, 3)
+        default:
+          if constexpr (KR >= 5) {
+            switch (st.code) {
+              QLS_MUX_CASE(4)
+              QLS_G1_CASE(4)
+              QLS_G2_CASE(0, 4)
+              QLS_G2_CASE(1, 4)
+              QLS_G2_CASE(2, 4)
+              QLS_G2_CASE(3, 4)
+            }
+          }
+          break;
+#undef QLS_MUX_CASE
+#undef QLS_G1_CASE
+#undef QLS_G2_CASE
       }
+      if (st.code == RS_C_STORE_D || st.code == RS_C_STORE_S) break;  // the tile is back in HBM
     }
   }
 }
 
-template <typename R, int T, int KR>
+template <typename R, int T, int KR, int CTAS>
 int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local, uint64_t index_offset,
               cudaStream_t stream) {
   using V = typename Vec2<R>::type;
+  constexpr int RS_THREADS = 1 << (T - KR);
   const int fixed = __builtin_popcountll(p.fix_mask);
   const int free_bits = n_local - p.tile_bits - fixed;
   QLS_ARG(free_bits >= 0 && free_bits < 40, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
   const uint64_t n_tiles = 1ull << free_bits;
   const int n_stages = p.pad >> 8;  // counted by qls_program_create
   const size_t smem = ((size_t)sizeof(V) << T) + (sizeof(uint64_t) << p.n_high) + (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
-  QLS_ARG(smem <= 112 * 1024, "register-stage pass needs %zu bytes of shared memory", smem);
-  auto kern = qls_rs_pass_kernel<R, T, KR>;
+  QLS_ARG(smem <= (size_t)(224 / CTAS) * 1024, "register-stage pass needs %zu bytes of shared memory", smem);
+  auto kern = qls_rs_pass_kernel<R, T, KR, CTAS>;
   static bool attr_set[64] = {false};
   static int sm_count[64] = {0};
   if (!attr_set[prog->device & 63]) {
-    QLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    QLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (224 / CTAS) * 1024));
     QLS_CUDA(cudaDeviceGetAttribute(&sm_count[prog->device & 63], cudaDevAttrMultiProcessorCount, prog->device));
     attr_set[prog->device & 63] = true;
   }
   // the pass description goes to constant memory; stream order keeps it alive for exactly this launch
   QLS_CUDA(cudaMemcpyToSymbolAsync(c_img, prog->rs_img_dev + prog->rs_img_off[pass_index], prog->rs_img_bytes[pass_index], 0,
                                    cudaMemcpyDeviceToDevice, stream));
-  uint64_t grid = 2ull * (uint64_t)sm_count[prog->device & 63];
+  uint64_t grid = (uint64_t)CTAS * (uint64_t)sm_count[prog->device & 63];
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<(unsigned)grid, RS_THREADS, smem, stream>>>(reinterpret_cast<V*>(state), index_offset, n_tiles, prog->pool_dev);
+  const char* dbg_env = getenv("QLS_RS_DEBUG");
+  kern<<<(unsigned)grid, RS_THREADS, smem, stream>>>(reinterpret_cast<V*>(state), index_offset, n_tiles, prog->pool_dev,
+                                                     dbg_env ? (uint32_t)atoi(dbg_env) : 0u);
   QLS_CUDA(cudaGetLastError());
   return QLS_OK;
 }
@@ -520,65 +524,139 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
 }  // namespace
 
 // Build the constant-memory image of every pass that has a register-stage form: header, micro-op
-// records, and the G1/G2 matrices (their pool_off re-based to the image body).  A pass whose image
-// would not fit gets size 0 and keeps the sweep form.  Host arrays; called by qls_program_create.
+// records (STAGE records get their ordinal in pool_off), the G1/G2 matrices, and one straight-line
+// step list per VARIANT = assignment of the pass's control qubits outside the tile.  A variant's list
+// holds only the ops that fire for it, enters a stage only if one of its ops fires (LOAD before the
+// first, TRANS between, STORE after the last) and is marked RS_IDLE when nothing fires.  A pass with
+// more than RS_MAX_CBITS such control qubits, or whose image would not fit, gets size 0 and keeps
+// the sweep form.  Host arrays; called by qls_program_create.
 int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsigned char* pool_host) {
   const size_t esz = prog->dtype == QLS_C128 ? 16 : 8;
   std::vector<unsigned char> all;
   prog->rs_img_off = new uint64_t[prog->n_passes ? prog->n_passes : 1];
   prog->rs_img_bytes = new uint32_t[prog->n_passes ? prog->n_passes : 1];
+  prog->rs_img_kr = new uint8_t[prog->n_passes ? prog->n_passes : 1];
   for (uint32_t i = 0; i < prog->n_passes; ++i) {
     const QlsPass& p = prog->passes_host[i];
     prog->rs_img_off[i] = all.size();
     prog->rs_img_bytes[i] = 0;
+    prog->rs_img_kr[i] = 0;
     const int n_stages = (int)(p.pad >> 8);
     if (p.rs_count == 0 || p.rs_count > (uint32_t)RS_MAX_OPS || n_stages < 1 || n_stages > RS_MAX_STAGES) continue;
-    std::vector<unsigned char> img(sizeof(RsHeader) + (size_t)p.rs_count * sizeof(QlsRsOp), 0);
+    const int KR = (rs_ops_host[p.rs_begin].flags & QLS_RS_FLAG_KR5) ? 5 : 4;  // first record is a STAGE (checked by create)
+    if (prog->dtype == QLS_C64 && KR != 5) continue;
     RsHeader h;
     memset(&h, 0, sizeof(h));
     h.L = p.low_bits;
     h.n_high = p.n_high;
     h.n_fseg = p.n_fseg;
-    h.n_ops = (int32_t)p.rs_count;
+    h.n_recs = (int32_t)p.rs_count;
     h.fix_val = p.fix_val;
     h.n_stages = n_stages;
     memcpy(h.high, p.high, sizeof(h.high));
     memcpy(h.fseg, p.fseg, sizeof(h.fseg));
-    bool skippable = true;
-    int n_xc = 0;
-    for (uint32_t o = 0; o < p.rs_count; ++o) {
-      QlsRsOp op = rs_ops_host[p.rs_begin + o];
+
+    std::vector<QlsRsOp> recs(rs_ops_host + p.rs_begin, rs_ops_host + p.rs_begin + p.rs_count);
+    std::vector<unsigned char> mats;  // 16-byte aligned matrix store
+    std::vector<uint16_t> moff(recs.size(), 0), code(recs.size(), 0);
+    uint64_t cmask = 0;
+    bool ok = true;
+    int ordinal = 0;
+    for (size_t o = 0; o < recs.size() && ok; ++o) {
+      QlsRsOp& op = recs[o];
+      if (op.kind == QLS_RS_STAGE) {
+        op.pool_off = (uint64_t)ordinal++;
+        ok = (((op.flags & QLS_RS_FLAG_KR5) ? 5 : 4) == KR);  // one register width per pass
+        continue;
+      }
+      // controls on pass-level fixed bits hold for every tile of the pass (or never: the op is dead)
+      if ((op.xc_val & p.fix_mask & op.xc_mask) != (p.fix_val & op.xc_mask & p.fix_mask)) {
+        op.xc_mask = ~0ull;  // never fires
+        op.xc_val = 0;
+        op.kind = QLS_RS_DIAG;
+        code[o] = 0;
+        continue;
+      }
+      op.xc_mask &= ~p.fix_mask;
+      op.xc_val &= ~p.fix_mask;
+      cmask |= op.xc_mask;
+      const bool real = (op.flags & QLS_OP_FLAG_REAL) != 0;
+      const bool ctl = (op.ctl_tmask | op.ctl_rmask) != 0;
       if (op.kind == QLS_RS_G1 || op.kind == QLS_RS_G2) {
         const size_t bytes = esz * (op.kind == QLS_RS_G1 ? 4 : 16);
-        const size_t off = img.size();
-        img.resize(off + bytes);
-        memcpy(img.data() + off, pool_host + op.pool_off, bytes);
-        op.pool_off = off - sizeof(RsHeader);
-      }
-      if (op.kind != QLS_RS_STAGE) {
-        if (op.xc_mask == 0) {
-          skippable = false;
-        } else if (skippable) {
-          int j = 0;
-          while (j < n_xc && !(h.xc_mask[j] == op.xc_mask && h.xc_val[j] == op.xc_val)) ++j;
-          if (j == n_xc) {
-            if (n_xc == RS_MAX_XC) {
-              skippable = false;
-            } else {
-              h.xc_mask[n_xc] = op.xc_mask;
-              h.xc_val[n_xc] = op.xc_val;
-              ++n_xc;
-            }
-          }
+        while (mats.size() % 16) mats.push_back(0);
+        moff[o] = 0;  // patched below once the matrix base is known
+        const size_t off = mats.size();
+        mats.resize(off + bytes);
+        memcpy(mats.data() + off, pool_host + op.pool_off, bytes);
+        op.pool_off = off;  // relative to the matrix store for now
+        if (op.kind == QLS_RS_G1) {
+          ok = op.r[0] < KR;
+          code[o] = (uint16_t)(RS_C_G1 + 4 * op.r[0] + (real ? 2 : 0) + (ctl ? 1 : 0));
+        } else {
+          ok = op.r[0] < op.r[1] && op.r[1] < KR;
+          code[o] = (uint16_t)(RS_C_G2 + 4 * rs_pair(op.r[0], op.r[1]) + (real ? 2 : 0) + (ctl ? 1 : 0));
         }
+      } else if (op.kind == QLS_RS_MUXRY) {
+        ok = op.r[0] < KR;
+        code[o] = (uint16_t)(RS_C_MUX + op.r[0]);
+      } else {
+        bool reg_bits = op.ctl_rmask != 0;
+        for (int j = 0; j < KR; ++j) reg_bits |= op.rt[1 << j] != 0;
+        code[o] = reg_bits ? RS_C_DIAG : RS_C_DIAG1;
       }
-      memcpy(img.data() + sizeof(RsHeader) + (size_t)o * sizeof(QlsRsOp), &op, sizeof(op));
     }
-    h.n_xc = skippable ? n_xc : 0;
+    if (!ok || __builtin_popcountll(cmask) > RS_MAX_CBITS) continue;
+    for (int b = 0; b < 64; ++b)
+      if ((cmask >> b) & 1) h.cbit[h.n_cbits++] = (uint8_t)b;
+
+    const size_t recs_bytes = recs.size() * sizeof(QlsRsOp);
+    const size_t mats_off = recs_bytes;  // body offset; sizeof(QlsRsOp) is a multiple of 16
+    for (size_t o = 0; o < recs.size(); ++o)
+      if (recs[o].kind == QLS_RS_G1 || recs[o].kind == QLS_RS_G2) moff[o] = (uint16_t)((mats_off + recs[o].pool_off) / 16);
+    while (mats.size() % 16) mats.push_back(0);
+
+    std::vector<RsStep> steps;
+    for (uint32_t v = 0; v < (1u << h.n_cbits); ++v) {
+      uint64_t assign = 0;
+      for (int j = 0; j < h.n_cbits; ++j) assign |= (uint64_t)((v >> j) & 1u) << h.cbit[j];
+      const size_t first = steps.size();
+      int cur = -1, pend = -1;
+      for (size_t o = 0; o < recs.size(); ++o) {
+        const QlsRsOp& op = recs[o];
+        if (op.kind == QLS_RS_STAGE) {
+          pend = (int)o;
+          continue;
+        }
+        if ((assign & op.xc_mask) != op.xc_val || pend < 0) continue;
+        if (pend != cur) {
+          const bool direct = (recs[pend].flags & QLS_RS_FLAG_DIRECT) != 0;
+          RsStep st = {0, (uint16_t)pend, (uint16_t)(cur < 0 ? 0 : cur), 0};
+          st.code = cur < 0 ? (direct ? RS_C_LOAD_D : RS_C_LOAD_S) : RS_C_TRANS;
+          steps.push_back(st);
+          cur = pend;
+        }
+        steps.push_back(RsStep{code[o], (uint16_t)o, 0, moff[o]});
+      }
+      if (cur < 0) {
+        h.vstart[v] = RS_IDLE;
+        continue;
+      }
+      const bool direct = (recs[cur].flags & QLS_RS_FLAG_DIRECT) != 0;
+      steps.push_back(RsStep{(uint16_t)(direct ? RS_C_STORE_D : RS_C_STORE_S), (uint16_t)cur, 0, 0});
+      h.vstart[v] = (uint16_t)first;
+    }
+    h.steps_off = (uint32_t)(recs_bytes + mats.size());
+    const size_t total = sizeof(RsHeader) + recs_bytes + mats.size() + steps.size() * sizeof(RsStep);
+    if (total > (size_t)RS_IMG_BYTES || steps.size() >= RS_IDLE || (mats_off + mats.size()) / 16 > 0xFFFFu) continue;
+    std::vector<unsigned char> img(total, 0);
     memcpy(img.data(), &h, sizeof(h));
+    memcpy(img.data() + sizeof(RsHeader), recs.data(), recs_bytes);
+    memcpy(img.data() + sizeof(RsHeader) + recs_bytes, mats.data(), mats.size());
+    memcpy(img.data() + sizeof(RsHeader) + h.steps_off, steps.data(), steps.size() * sizeof(RsStep));
     while (img.size() % 16) img.push_back(0);
-    if (img.size() > (size_t)RS_IMG_BYTES) continue;
     prog->rs_img_bytes[i] = (uint32_t)img.size();
+    prog->rs_img_kr[i] = (uint8_t)KR;
     all.insert(all.end(), img.begin(), img.end());
   }
   prog->rs_img_dev = nullptr;
@@ -597,6 +675,9 @@ bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_ind
 
 int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
                        uint64_t index_offset, cudaStream_t stream) {
-  if (prog->dtype == QLS_C128) return launch_rs<double, 12, 4>(prog, p, pass_index, state, n_local, index_offset, stream);
-  return launch_rs<float, 13, 5>(prog, p, pass_index, state, n_local, index_offset, stream);
+  if (prog->dtype == QLS_C128) {
+    if (prog->rs_img_kr[pass_index] == 5) return launch_rs<double, 12, 5, RS_CTAS_F64_KR5>(prog, p, pass_index, state, n_local, index_offset, stream);
+    return launch_rs<double, 12, 4, 2>(prog, p, pass_index, state, n_local, index_offset, stream);
+  }
+  return launch_rs<float, 13, 5, 2>(prog, p, pass_index, state, n_local, index_offset, stream);
 }

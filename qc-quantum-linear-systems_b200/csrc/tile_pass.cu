@@ -203,6 +203,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   p->rs_img_dev = nullptr;
   p->rs_img_off = nullptr;
   p->rs_img_bytes = nullptr;
+  p->rs_img_kr = nullptr;
   for (uint32_t i = 0; i < n_passes; ++i) {
     p->passes_host[i] = passes_host[i];
     QlsPass& ps = p->passes_host[i];
@@ -259,6 +260,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
     if (p->rs_img_dev) cudaFree(p->rs_img_dev);
     delete[] p->rs_img_off;
     delete[] p->rs_img_bytes;
+    delete[] p->rs_img_kr;
     if (p->ops_dev) cudaFree(p->ops_dev);
     if (p->rs_ops_dev) cudaFree(p->rs_ops_dev);
     if (p->pool_dev) cudaFree(p->pool_dev);
@@ -279,6 +281,7 @@ extern "C" int qls_program_destroy(QlsProgram* prog) {
   if (prog->rs_img_dev) cudaFree(prog->rs_img_dev);
   delete[] prog->rs_img_off;
   delete[] prog->rs_img_bytes;
+  delete[] prog->rs_img_kr;
   delete[] prog->passes_host;
   delete prog;
   return QLS_OK;

@@ -18,6 +18,8 @@ The input circuit is never mutated (QASM / depth / width come from the un-fused 
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from dataclasses import dataclass, field
@@ -384,6 +386,7 @@ class LoweringOptions:
     n_local: int = 0  # 0 -> all qubits local (single GPU)
     batch: bool = False  # one whole-state pass for qls_batch_expect_z (parameterised, n <= 12/13)
     register_stages: bool = True  # also emit the register-stage form of passes that can use it
+    rs_reg_qubits: int = 0  # register qubits per thread in the register-stage form: 0 -> default (5); fp64 also allows 4
 
     def resolved_tile_bits(self) -> int:
         return self.tile_bits or (12 if self.dtype == "fp64" else 13)
@@ -490,7 +493,11 @@ class _Emitter:
         self.ops: List[_abi.QlsOp] = []
         self.rs_ops: List[_abi.QlsRsOp] = []
         self.rs_T = 12 if opts.dtype == "fp64" else 13
-        self.rs_KR = self.rs_T - 8  # 256 threads index 8 tile bits; 2^KR amplitudes per thread
+        # 2^KR amplitudes per thread, 2^(T - KR) threads per tile (csrc/rs_pass.cu): complex64 always 5;
+        # complex128 5 (128 threads x 32 amplitudes: a whole 5-qubit block per stage) or 4 (256 x 16)
+        self.rs_KR = 5 if opts.dtype == "fp32" else (opts.rs_reg_qubits or int(os.environ.get("QLS_RS_KR", "5")))
+        if self.rs_KR not in (4, 5):
+            raise ValueError("rs_reg_qubits must be 4 or 5")
         self.pool = bytearray()
         self.pass_info: List[PassInfo] = []
         self.steps: List[Step] = []
@@ -551,9 +558,42 @@ class _Emitter:
         self.cur.append(b)
         self.cur_high |= need
 
+    MAX_EXT_CONTROLS = 6  # csrc/rs_pass.cu keeps one step list per assignment of the controls outside the tile
+
+    def _ctl_prefix(self, blocks: Sequence[Block]) -> int:
+        """Largest k such that blocks[:k] have at most MAX_EXT_CONTROLS distinct control qubits outside
+        the qubits they touch (controls shared by all of them become pass-level fixed bits: free)."""
+        touched: set = set()
+        ctl: Dict[int, set] = {}
+        common: Optional[Dict[int, int]] = None
+        for k, b in enumerate(blocks):
+            touched |= set(b.touched)
+            bc = dict(b.controls) if b.kind in ("dense", "diag") else {}
+            for q, v in bc.items():
+                ctl.setdefault(q, set()).add(v)
+            common = bc if common is None else {q: v for q, v in common.items() if bc.get(q) == v}
+            ext = [q for q in ctl if q not in touched and q not in common]
+            if len(ext) > self.MAX_EXT_CONTROLS:
+                return max(k, 1)
+        return len(blocks)
+
     def flush(self) -> None:
         if not self.cur:
             return
+        if not self.opts.batch and self.opts.register_stages:
+            k = self._ctl_prefix(self.cur)
+            if k < len(self.cur):
+                rest = self.cur[k:]
+                self.cur = self.cur[:k]
+                self.cur_high = set().union(*[set(b.touched) for b in self.cur])
+                self._flush_one()
+                self.cur = rest
+                self.cur_high = set().union(*[set(b.touched) for b in self.cur])
+                self.flush()
+                return
+        self._flush_one()
+
+    def _flush_one(self) -> None:
         blocks, self.cur = tensor_merge(self.cur, self.opts.max_fuse_qubits), []
         needed = set(self.cur_high)
         self.cur_high = set()
@@ -704,6 +744,7 @@ class _Emitter:
                     st.r[j] = p_
                 if KR > 4:
                     st.pad0 = regq_sorted[4]
+                    st.flags |= 0x20  # five register qubits
                 if min(regq_sorted) >= 5:
                     st.flags |= 0x10  # direct global <-> register access is coalesced (lanes = tile bits 0..4)
                 segs = _segments([(j, p_) for j, p_ in enumerate(tpos)])

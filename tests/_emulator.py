@@ -33,7 +33,7 @@ def run_pass_rs(state, p, rs_ops, pool, cdtype, n_local, index_offset=0):
     is re-read per stage as a[thread][register combo]."""
     T, L = p.tile_bits, p.low_bits
     sh = 0 if np.dtype(cdtype).itemsize == 16 else 1
-    KR = T - 8
+    KR = 5 if (rs_ops[p.rs_begin].flags & 0x20) else 4  # STAGE flag: five register qubits
     A = 2**KR
     NT = 2 ** (T - KR)
     fixed = bin(p.fix_mask).count("1")
