@@ -16,8 +16,7 @@
 //     matrix element straight from a uniform register: no per-thread load in the inner loops;
 //   * stages are entered lazily: a stage whose ops are all switched off for this tile by controls
 //     outside the tile costs nothing, and a tile on which no op fires is neither read nor written;
-//   * the next tile of the CTA is prefetched into L2 (cp.async.bulk.prefetch) while the current
-//     one is in registers, so the HBM read latency is off the critical path;
+//   * tile loads/stores are streaming (ld/st.global.cs, cp.async.cg) so that L1 keeps the phase tables;
 //   * diagonal tables / multiplexer angles are fetched in batches before they are used.
 #include <stdlib.h>
 #include <string.h>
@@ -29,9 +28,6 @@
 namespace {
 
 constexpr int RS_MAX_OPS = 160;
-#ifndef RS_CTAS_F64_KR5
-#define RS_CTAS_F64_KR5 2
-#endif
 constexpr int RS_MAX_STAGES = 24;
 constexpr int RS_MAX_CBITS = 6;
 constexpr int RS_IMG_BYTES = 60 * 1024;
@@ -71,8 +67,10 @@ enum {
   RS_C_DIAG1 = 7,    // one phase per thread
   RS_C_MUX = 8,      // + register qubit
   RS_C_G1 = 16,      // + 4 * register qubit + 2 * real + ctl
-  RS_C_G2 = 64       // + 4 * pair + 2 * real + ctl
+  RS_C_G2 = 64,      // + 4 * pair + 2 * real + ctl
+  RS_C_ACQ = 15      // take the SM's FP64 token (two-group kernels): a run of heavy ops follows
 };
+constexpr uint16_t RS_F_RELEASE = 1;  // RsStep.moff of TRANS / STORE_*: hand the FP64 token back first
 constexpr uint16_t RS_IDLE = 0xFFFFu;
 
 // pair index of register qubits p < q: the six pairs below 4 first (KR = 4), then (p, 4)
@@ -103,10 +101,6 @@ __device__ __forceinline__ uint32_t rs_addr(uint32_t base, const uint32_t (&c)[K
   for (int j = 0; j < KR; ++j)
     if ((r >> j) & 1) a ^= c[j];
   return a;
-}
-
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 // ---- micro-ops on the register tile ------------------------------------------------------------------
@@ -205,11 +199,12 @@ __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* _
   for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
   constexpr int CH = 4;  // phases fetched per batch (register budget)
+  const V* tb = table + ti0;  // the register-qubit fields are disjoint from ti0: | is +, and they are warp-uniform
 #pragma unroll
   for (int c = 0; c < A; c += CH) {
     V ph[CH];
 #pragma unroll
-    for (int r = 0; r < CH; ++r) ph[r] = __ldg(&table[rs_tidx<KR>(ti0, d, c + r)]);  // index is valid whatever the controls say
+    for (int r = 0; r < CH; ++r) ph[r] = __ldg(tb + rs_tidx<KR>(0u, d, c + r));  // index is valid whatever the controls say
 #pragma unroll
     for (int r = 0; r < CH; ++r)
       if (tok && (((uint32_t)(c + r) & rm) == rv)) a[c + r] = cmul(a[c + r], ph[r]);
@@ -223,6 +218,7 @@ __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* 
   for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
   constexpr int CH = 4;
+  const V* tb = table + ti0;
 #pragma unroll
   for (int c = 0; c < A / 2; c += CH) {
     V cs[CH];
@@ -230,7 +226,7 @@ __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* 
     for (int q = 0; q < CH; ++q) {
       const int p = c + q;
       const int i0 = ((p >> RQ) << (RQ + 1)) | (p & ((1 << RQ) - 1));
-      cs[q] = __ldg(&table[rs_tidx<KR>(ti0, d, i0)]);
+      cs[q] = __ldg(tb + rs_tidx<KR>(0u, d, i0));
     }
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
@@ -274,8 +270,19 @@ __device__ __forceinline__ uint32_t rs_variant(uint64_t gbase) {
 // loop on the uniform datapath only if it can PROVE every branch around a barrier warp-uniform; a
 // warp shuffle of the step counter makes that proof trivial (loop-carried state it cannot see
 // through makes it fall back to per-thread LDC + vector-register operands, and the kernel spills).
-template <typename R, int T, int KR, int CTAS>
-__global__ void __launch_bounds__(1 << (T - KR), CTAS)
+// GROUPS = 2: one CTA per SM holds TWO warp-groups, each working on its own tile in its own 64 KB of
+// shared memory with its own named barrier.  Identical CTAs that merely share an SM fall into
+// lockstep (whoever gets ahead leaves the FP64 pipe to the other one, which then catches up), so
+// HBM, shared-memory and FP64 phases add up instead of overlapping (measured: profiles/).  The two
+// groups therefore pass an FP64 token (RS_C_ACQ / RS_F_RELEASE steps placed by the host around runs
+// of heavy ops): while one group computes, the other one loads, re-distributes or stores.
+template <int ID_BASE>
+__device__ __forceinline__ void rs_group_sync(uint32_t group, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(ID_BASE + group), "r"(threads) : "memory");
+}
+
+template <typename R, int T, int KR, int CTAS, int GROUPS>
+__global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
     qls_rs_pass_kernel(typename Vec2<R>::type* __restrict__ state, const uint64_t index_offset, const uint64_t n_tiles,
                        const unsigned char* __restrict__ pool, const uint32_t dbg) {
   using V = typename Vec2<R>::type;
@@ -286,54 +293,42 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
   constexpr int UNITS = (1 << T) / APU;  // 4096
   constexpr uint32_t TILE_BYTES = (uint32_t)sizeof(V) << T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  V* sm = reinterpret_cast<V*>(smem_raw);
-  uint4* sm16 = reinterpret_cast<uint4*>(smem_raw);
-  uint64_t* hoff = reinterpret_cast<uint64_t*>(smem_raw + TILE_BYTES);  // [1 << n_high]
+  __shared__ int fp64_token;  // 0: free
+  // warp-group of this thread (provably warp-uniform for ptxas: shuffle) and its thread index inside it
+  const uint32_t grp = GROUPS == 1 ? 0u : __shfl_sync(0xffffffffu, threadIdx.x >> (T - KR), 0);
+  const int tid = threadIdx.x & (RS_THREADS - 1);
+  V* sm = reinterpret_cast<V*>(smem_raw + (size_t)grp * TILE_BYTES);
+  uint4* sm16 = reinterpret_cast<uint4*>(smem_raw + (size_t)grp * TILE_BYTES);
+  uint64_t* hoff = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GROUPS * TILE_BYTES);  // [1 << n_high]
   uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << c_img.h.n_high));  // [stages][RS_THREADS]
+#define RS_SYNC() do { if (GROUPS == 1) __syncthreads(); else rs_group_sync<1>(grp, RS_THREADS); } while (0)
 
   const QlsRsOp* recs = reinterpret_cast<const QlsRsOp*>(c_img.body);
-  const int tid = threadIdx.x;
   const int L = c_img.h.L;
   const int n_recs = c_img.h.n_recs;
   const int n_high = c_img.h.n_high;
   const int n_fseg = c_img.h.n_fseg;
 
   // ---- once per CTA: high-qubit spread table, per-stage thread -> swizzled tile offset ----------------
-  for (int r = tid; r < (1 << n_high); r += RS_THREADS) {
+  for (int r = threadIdx.x; r < (1 << n_high); r += GROUPS * RS_THREADS) {
     uint64_t g = 0;
     for (int j = 0; j < n_high; ++j) g |= (uint64_t)((r >> j) & 1) << c_img.h.high[j];
     hoff[r] = g;
   }
-  for (int o = 0; o < n_recs; ++o) {
+  if (threadIdx.x == 0) fp64_token = 0;
+  for (int o = 0; o < n_recs && threadIdx.x < RS_THREADS; ++o) {
     if (recs[o].kind == QLS_RS_STAGE) {
       const uint32_t tb = gather_segs32((uint32_t)tid, recs[o].tseg, recs[o].n_tseg);
       ptb[(uint32_t)recs[o].pool_off * RS_THREADS + tid] = (uint16_t)swz<SH>(tb);  // pool_off of a STAGE = its ordinal
     }
   }
-  // L2 prefetch geometry: the tile is 2^n_high runs of 2^L amplitudes; units of <= 4 KB
-  const uint32_t run_bytes = (uint32_t)sizeof(V) << L;
-  const uint32_t pf_bytes = run_bytes < 4096u ? run_bytes : 4096u;
-  const uint32_t pf_units = TILE_BYTES / pf_bytes;
-  const uint32_t pf_per_run_log = 31 - __clz(run_bytes / pf_bytes);
   __syncthreads();
 
   // ---- persistent loop over tiles ------------------------------------------------------------------
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const uint64_t tile_stride = (uint64_t)GROUPS * gridDim.x;
+  for (uint64_t tile = (uint64_t)GROUPS * blockIdx.x + grp; tile < n_tiles; tile += tile_stride) {
     const uint64_t base = gather_segs64(tile, c_img.h.fseg, n_fseg) | c_img.h.fix_val;
     const uint64_t gbase = base | index_offset;
-    {  // next tile of this CTA -> L2
-      const uint64_t nt = tile + gridDim.x;
-      if (nt < n_tiles) {
-        const uint64_t nbase = gather_segs64(nt, c_img.h.fseg, n_fseg) | c_img.h.fix_val;
-        if (c_img.h.vstart[rs_variant(nbase | index_offset)] != RS_IDLE) {
-          for (uint32_t u = tid; u < pf_units; u += RS_THREADS) {
-            const uint64_t g = nbase | hoff[u >> pf_per_run_log];
-            prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(&state[g]) + (size_t)(u & ((1u << pf_per_run_log) - 1u)) * pf_bytes,
-                             pf_bytes);
-          }
-        }
-      }
-    }
     uint32_t s = __shfl_sync(0xffffffffu, (uint32_t)c_img.h.vstart[rs_variant(gbase)], 0);
     if (s == RS_IDLE) continue;  // no op fires on this tile: neither read nor written
     const RsStep* steps = reinterpret_cast<const RsStep*>(c_img.body + c_img.h.steps_off);
@@ -356,7 +351,7 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
 #pragma unroll
           for (int r = 0; r < A; ++r) {
             const uint32_t idx = rs_addr<KR>(ltb, lq, r);
-            a[r] = state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]];
+            a[r] = __ldcs(&state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]]);  // streaming: keep L1 for the tables
           }
           break;
         }
@@ -364,7 +359,7 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
           uint32_t cq[KR], lq[KR];
           rs_stage_bits<KR, SH>(op, cq, lq);
           const uint32_t mytb = ptb[(uint32_t)op.pool_off * RS_THREADS + tid];
-          __syncthreads();  // the previous tile's write-back has left shared memory
+          RS_SYNC();  // the previous tile's write-back has left shared memory
 #pragma unroll 4
           for (int u = tid; u < UNITS; u += RS_THREADS) {
             const int i = u * APU;
@@ -373,7 +368,7 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
           }
           cp_async_commit();
           cp_async_wait<0>();
-          __syncthreads();
+          RS_SYNC();
 #pragma unroll
           for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
           break;
@@ -383,24 +378,29 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
           uint32_t cq[KR], lq[KR];
           rs_stage_bits<KR, SH>(from, cq, lq);
           uint32_t mytb = ptb[(uint32_t)from.pool_off * RS_THREADS + tid];
-          __syncthreads();  // every thread is done with the previous shared-memory image
+          RS_SYNC();  // every thread is done with the previous shared-memory image (and with its FP64 run)
+          if (GROUPS > 1 && st.moff == RS_F_RELEASE && tid == 0) atomicExch(&fp64_token, 0);
 #pragma unroll
           for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
           rs_stage_bits<KR, SH>(op, cq, lq);
           mytb = ptb[(uint32_t)op.pool_off * RS_THREADS + tid];
-          __syncthreads();
+          RS_SYNC();
 #pragma unroll
           for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
           break;
         }
         case RS_C_STORE_D: {
+          if (GROUPS > 1 && st.moff == RS_F_RELEASE) {
+            RS_SYNC();
+            if (tid == 0) atomicExch(&fp64_token, 0);
+          }
           uint32_t cq[KR], lq[KR];
           rs_stage_bits<KR, SH>(op, cq, lq);
           const uint32_t ltb = swz<SH>(ptb[(uint32_t)op.pool_off * RS_THREADS + tid]);
 #pragma unroll
           for (int r = 0; r < A; ++r) {
             const uint32_t idx = rs_addr<KR>(ltb, lq, r);
-            state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]] = a[r];
+            __stcs(&state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]], a[r]);
           }
           break;
         }
@@ -408,15 +408,25 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
           uint32_t cq[KR], lq[KR];
           rs_stage_bits<KR, SH>(op, cq, lq);
           const uint32_t mytb = ptb[(uint32_t)op.pool_off * RS_THREADS + tid];
-          __syncthreads();
+          RS_SYNC();
+          if (GROUPS > 1 && st.moff == RS_F_RELEASE && tid == 0) atomicExch(&fp64_token, 0);
 #pragma unroll
           for (int r = 0; r < A; ++r) sm[rs_addr<KR>(mytb, cq, r)] = a[r];
-          __syncthreads();
+          RS_SYNC();
 #pragma unroll 4
           for (int u = tid; u < UNITS; u += RS_THREADS) {
             const int i = u * APU;
             const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
-            *reinterpret_cast<uint4*>(&state[g]) = sm16[swz<SH>((uint32_t)i) >> SH];
+            __stcs(reinterpret_cast<uint4*>(&state[g]), sm16[swz<SH>((uint32_t)i) >> SH]);
+          }
+          break;
+        }
+        case RS_C_ACQ: {
+          if (GROUPS > 1) {
+            if (tid == 0) {
+              while (atomicCAS(&fp64_token, 0, 1) != 0) __nanosleep(32);
+            }
+            RS_SYNC();
           }
           break;
         }
@@ -489,7 +499,9 @@ __global__ void __launch_bounds__(1 << (T - KR), CTAS)
   }
 }
 
-template <typename R, int T, int KR, int CTAS>
+#undef RS_SYNC
+
+template <typename R, int T, int KR, int CTAS, int GROUPS>
 int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local, uint64_t index_offset,
               cudaStream_t stream) {
   using V = typename Vec2<R>::type;
@@ -499,9 +511,9 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
   QLS_ARG(free_bits >= 0 && free_bits < 40, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
   const uint64_t n_tiles = 1ull << free_bits;
   const int n_stages = p.pad >> 8;  // counted by qls_program_create
-  const size_t smem = ((size_t)sizeof(V) << T) + (sizeof(uint64_t) << p.n_high) + (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
+  const size_t smem = ((size_t)GROUPS * sizeof(V) << T) + (sizeof(uint64_t) << p.n_high) + (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
   QLS_ARG(smem <= (size_t)(224 / CTAS) * 1024, "register-stage pass needs %zu bytes of shared memory", smem);
-  auto kern = qls_rs_pass_kernel<R, T, KR, CTAS>;
+  auto kern = qls_rs_pass_kernel<R, T, KR, CTAS, GROUPS>;
   static bool attr_set[64] = {false};
   static int sm_count[64] = {0};
   if (!attr_set[prog->device & 63]) {
@@ -513,9 +525,9 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
   QLS_CUDA(cudaMemcpyToSymbolAsync(c_img, prog->rs_img_dev + prog->rs_img_off[pass_index], prog->rs_img_bytes[pass_index], 0,
                                    cudaMemcpyDeviceToDevice, stream));
   uint64_t grid = (uint64_t)CTAS * (uint64_t)sm_count[prog->device & 63];
-  if (grid > n_tiles) grid = n_tiles;
+  if (grid * GROUPS > n_tiles) grid = (n_tiles + GROUPS - 1) / GROUPS;
   const char* dbg_env = getenv("QLS_RS_DEBUG");
-  kern<<<(unsigned)grid, RS_THREADS, smem, stream>>>(reinterpret_cast<V*>(state), index_offset, n_tiles, prog->pool_dev,
+  kern<<<(unsigned)grid, GROUPS * RS_THREADS, smem, stream>>>(reinterpret_cast<V*>(state), index_offset, n_tiles, prog->pool_dev,
                                                      dbg_env ? (uint32_t)atoi(dbg_env) : 0u);
   QLS_CUDA(cudaGetLastError());
   return QLS_OK;
@@ -532,6 +544,8 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
 // the sweep form.  Host arrays; called by qls_program_create.
 int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsigned char* pool_host) {
   const size_t esz = prog->dtype == QLS_C128 ? 16 : 8;
+  const char* lock_env = getenv("QLS_RS_LOCK_MIN");
+  const int lock_min = lock_env ? atoi(lock_env) : 4;  // lightest run of ops (in real-2x2 units) worth the FP64 token
   std::vector<unsigned char> all;
   prog->rs_img_off = new uint64_t[prog->n_passes ? prog->n_passes : 1];
   prog->rs_img_bytes = new uint32_t[prog->n_passes ? prog->n_passes : 1];
@@ -544,7 +558,7 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
     const int n_stages = (int)(p.pad >> 8);
     if (p.rs_count == 0 || p.rs_count > (uint32_t)RS_MAX_OPS || n_stages < 1 || n_stages > RS_MAX_STAGES) continue;
     const int KR = (rs_ops_host[p.rs_begin].flags & QLS_RS_FLAG_KR5) ? 5 : 4;  // first record is a STAGE (checked by create)
-    if (prog->dtype == QLS_C64 && KR != 5) continue;
+    if (KR != (prog->dtype == QLS_C64 ? 5 : 4)) continue;  // complex64: 32 amplitudes per thread, complex128: 16
     RsHeader h;
     memset(&h, 0, sizeof(h));
     h.L = p.low_bits;
@@ -644,6 +658,31 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
       }
       const bool direct = (recs[cur].flags & QLS_RS_FLAG_DIRECT) != 0;
       steps.push_back(RsStep{(uint16_t)(direct ? RS_C_STORE_D : RS_C_STORE_S), (uint16_t)cur, 0, 0});
+      // FP64 token: a run of ops between two data-movement steps that is heavy enough takes the token
+      // at its start (ACQ) and the movement step that ends it gives the token back (RS_F_RELEASE)
+      std::vector<RsStep> out;
+      for (size_t a = first; a < steps.size();) {
+        out.push_back(steps[a]);  // LOAD / TRANS (or the final STORE)
+        size_t b = a + 1;
+        int weight = 0;
+        while (b < steps.size() && steps[b].code >= RS_C_DIAG) {
+          const uint16_t c = steps[b].code;
+          if (c >= RS_C_G2) weight += (c & 2) ? 2 : 4;       // real : complex 4x4
+          else if (c >= RS_C_G1) weight += (c & 2) ? 1 : 2;  // real : complex 2x2
+          else weight += 1;                                  // diagonal / multiplexed RY
+          ++b;
+        }
+        if (b > a + 1 && weight >= lock_min && b < steps.size()) {
+          out.push_back(RsStep{RS_C_ACQ, 0, 0, 0});
+          out.insert(out.end(), steps.begin() + a + 1, steps.begin() + b);
+          steps[b].moff = RS_F_RELEASE;
+        } else {
+          out.insert(out.end(), steps.begin() + a + 1, steps.begin() + b);
+        }
+        a = b;
+      }
+      steps.resize(first);
+      steps.insert(steps.end(), out.begin(), out.end());
       h.vstart[v] = (uint16_t)first;
     }
     h.steps_off = (uint32_t)(recs_bytes + mats.size());
@@ -669,15 +708,22 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
 
 // true if pass `pass_index` of `prog` can run in register-stage form on a state of n_local qubits
 bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, int n_local) {
-  const int want_T = prog->dtype == QLS_C128 ? 12 : 13;
-  return prog->rs_img_bytes && prog->rs_img_bytes[pass_index] > 0 && p.tile_bits == want_T && n_local >= want_T;
+  const bool t_ok = prog->dtype == QLS_C128 ? (p.tile_bits == 12 || (p.tile_bits == 11 && prog->rs_img_kr[pass_index] == 4))
+                                            : p.tile_bits == 13;
+  return prog->rs_img_bytes && prog->rs_img_bytes[pass_index] > 0 && t_ok && n_local >= p.tile_bits;
 }
 
 int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
                        uint64_t index_offset, cudaStream_t stream) {
-  if (prog->dtype == QLS_C128) {
-    if (prog->rs_img_kr[pass_index] == 5) return launch_rs<double, 12, 5, RS_CTAS_F64_KR5>(prog, p, pass_index, state, n_local, index_offset, stream);
-    return launch_rs<double, 12, 4, 2>(prog, p, pass_index, state, n_local, index_offset, stream);
+  static int pingpong = -1;  // QLS_RS_PINGPONG=0: two independent CTAs per SM instead of two token-passing groups
+  if (pingpong < 0) {
+    const char* e = getenv("QLS_RS_PINGPONG");
+    pingpong = e ? atoi(e) : 0;
   }
-  return launch_rs<float, 13, 5, 2>(prog, p, pass_index, state, n_local, index_offset, stream);
+  if (prog->dtype == QLS_C128) {
+    if (p.tile_bits == 11) return launch_rs<double, 11, 4, 4, 1>(prog, p, pass_index, state, n_local, index_offset, stream);
+    if (pingpong) return launch_rs<double, 12, 4, 1, 2>(prog, p, pass_index, state, n_local, index_offset, stream);
+    return launch_rs<double, 12, 4, 2, 1>(prog, p, pass_index, state, n_local, index_offset, stream);
+  }
+  return launch_rs<float, 13, 5, 2, 1>(prog, p, pass_index, state, n_local, index_offset, stream);
 }

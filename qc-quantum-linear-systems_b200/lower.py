@@ -386,10 +386,13 @@ class LoweringOptions:
     n_local: int = 0  # 0 -> all qubits local (single GPU)
     batch: bool = False  # one whole-state pass for qls_batch_expect_z (parameterised, n <= 12/13)
     register_stages: bool = True  # also emit the register-stage form of passes that can use it
-    rs_reg_qubits: int = 0  # register qubits per thread in the register-stage form: 0 -> default (5); fp64 also allows 4
 
     def resolved_tile_bits(self) -> int:
-        return self.tile_bits or (12 if self.dtype == "fp64" else 13)
+        if self.tile_bits:
+            return self.tile_bits
+        if self.dtype == "fp64":
+            return int(os.environ.get("QLS_TILE_BITS", "0")) or 12
+        return 13
 
 
 @dataclass
@@ -492,12 +495,11 @@ class _Emitter:
         self.passes: List[_abi.QlsPass] = []
         self.ops: List[_abi.QlsOp] = []
         self.rs_ops: List[_abi.QlsRsOp] = []
-        self.rs_T = 12 if opts.dtype == "fp64" else 13
-        # 2^KR amplitudes per thread, 2^(T - KR) threads per tile (csrc/rs_pass.cu): complex64 always 5;
-        # complex128 5 (128 threads x 32 amplitudes: a whole 5-qubit block per stage) or 4 (256 x 16)
-        self.rs_KR = 5 if opts.dtype == "fp32" else (opts.rs_reg_qubits or int(os.environ.get("QLS_RS_KR", "5")))
-        if self.rs_KR not in (4, 5):
-            raise ValueError("rs_reg_qubits must be 4 or 5")
+        self.rs_T = opts.resolved_tile_bits()  # the register-stage kernel exists for 11 / 12 (complex128) and 13 (complex64)
+        # 2^KR amplitudes per thread, 2^(T - KR) threads per tile (csrc/rs_pass.cu): complex64 5, complex128 4
+        # (complex128 with 5 = 128 threads x 32 amplitudes halves the stage count but leaves 8 warps per SM:
+        # measured slower, profiles/README.md)
+        self.rs_KR = 5 if opts.dtype == "fp32" else 4
         self.pool = bytearray()
         self.pass_info: List[PassInfo] = []
         self.steps: List[Step] = []
@@ -671,7 +673,8 @@ class _Emitter:
 
         rs_begin = len(self.rs_ops)
         rs_stages = 0
-        if self.opts.register_stages and not self.opts.batch and T == self.rs_T:
+        rs_ok = self.rs_T in ((11, 12) if self.opts.dtype == "fp64" else (13,)) and not (self.rs_T == 11 and self.rs_KR != 4)
+        if self.opts.register_stages and not self.opts.batch and T == self.rs_T and rs_ok:
             rs_stages = self._emit_register_stages(blocks, local_pos, common)
         p = _abi.QlsPass()
         p.rs_begin, p.rs_count = rs_begin, len(self.rs_ops) - rs_begin
@@ -737,6 +740,9 @@ class _Emitter:
                 regq_sorted = sorted(regq)
                 rho = {p_: j for j, p_ in enumerate(regq_sorted)}
                 tpos = [p_ for p_ in range(T) if p_ not in regq]
+                direct = min(regq_sorted) >= 5
+                if not direct and self.opts.dtype == "fp64":
+                    tpos = self._conflict_free_lanes(tpos)
                 tbit = {p_: j for j, p_ in enumerate(tpos)}
                 st = _abi.QlsRsOp()
                 st.kind = _abi.QLS_RS_STAGE
@@ -745,7 +751,7 @@ class _Emitter:
                 if KR > 4:
                     st.pad0 = regq_sorted[4]
                     st.flags |= 0x20  # five register qubits
-                if min(regq_sorted) >= 5:
+                if direct:
                     st.flags |= 0x10  # direct global <-> register access is coalesced (lanes = tile bits 0..4)
                 segs = _segments([(j, p_) for j, p_ in enumerate(tpos)])
                 if len(segs) > _abi.QLS_MAX_SEG:
@@ -767,6 +773,27 @@ class _Emitter:
             del self.rs_ops[mark:]
             return 0
         return len(stages)
+
+    @staticmethod
+    def _conflict_free_lanes(tpos: List[int]) -> List[int]:
+        """Order of the thread bits of a stage that is exchanged through shared memory.  A 128-bit
+        access is served per quarter warp (lanes 0..7 = thread bits 0..2) and the swizzle of
+        csrc/rs_pass.cu puts 16-byte unit u into bank group (u ^ u>>3 ^ u>>6 ^ u>>9) & 7: the eight
+        lanes hit eight different groups iff the tile positions of thread bits 0..2 are pairwise
+        different mod 3.  Keep the ascending order when that already holds (or cannot be had)."""
+        if len({p_ % 3 for p_ in tpos[:3]}) == 3:
+            return tpos
+        pick: List[int] = []
+        for res in range(3):
+            cand = [p_ for p_ in tpos if p_ % 3 == res]
+            if not cand:
+                return tpos
+            pick.append(cand[0])
+        pick.sort()
+        out = pick + [p_ for p_ in tpos if p_ not in pick]
+        if len(_segments([(j, p_) for j, p_ in enumerate(out)])) > _abi.QLS_MAX_SEG:
+            return tpos
+        return out
 
     def _rs_controls(self, op: _abi.QlsRsOp, controls: Dict[int, int], local_pos, rho, tbit) -> None:
         for q, v in controls.items():
