@@ -28,7 +28,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "hhl_amp_updates_per_s"
-TRAFFIC_NOTE = None  # dram bytes per launch from an ncu --set full capture: see profiles/README.md
+
+
+def _traffic(algorithmic_bytes_per_launch: float):
+    """DRAM bytes per launch of the dominant kernel: the read+write / algorithmic ratio of the ncu
+    --set full capture summarised in profiles/traffic.json (tools/summarize_ncu.py), applied to this
+    run's launch size.  None if no capture is on file."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as fh:
+        t = json.load(fh)
+    return t["dram_bytes_per_algorithmic_byte"] * algorithmic_bytes_per_launch, t["source"]
+
 UNIT = "amp-updates/s"
 
 
@@ -278,10 +290,16 @@ def run_gpu(args):
         roofline = None
         if kern_ms:
             achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "qls_tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "peak_source": peak_src, "traffic": TRAFFIC_NOTE,
+            traffic, traffic_src = _traffic(kern_bytes / max(1, kern_launches))
+            fma = low.fp64_fma_count()
+            roofline = {"bound": "hbm", "kernel": "qls_rs_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                         "launches_per_step": kern_launches, "algorithmic_bytes_per_step": kern_bytes,
-                        "avg_launch_ms": kern_ms / max(1, kern_launches), "kernel_ms_per_step": kern_ms}
+                        "algorithmic_bytes_per_launch": kern_bytes / max(1, kern_launches),
+                        "avg_launch_ms": kern_ms / max(1, kern_launches), "kernel_ms_per_step": kern_ms,
+                        # second ceiling of the same kernel: the FP64 pipe (DFMA/s measured by tools/microbench/fp64_pipes.cu)
+                        "fp64": {"fma_per_step": fma, "achieved_tfma_s": fma / (kern_ms * 1e-3) / 1e12, "peak_tfma_s": 18.4,
+                                 "frac": fma / (kern_ms * 1e-3) / 18.4e12}}
         # CPU baseline on a bounded sample of the same workload (N = 1 only: torchrun pins OMP threads to 1)
         cpu = None
         if world == 1:

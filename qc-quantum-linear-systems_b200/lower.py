@@ -453,6 +453,22 @@ class LoweredProgram:
     def total_pass_bytes(self) -> int:
         return sum(self.pass_bytes(i) for i in range(self.n_passes))
 
+    def fp64_fma_count(self, n_local: Optional[int] = None) -> float:
+        """Real fused multiply-adds of the register-stage form (complex 4x4: 16 per amplitude, real
+        4x4: 8, complex 2x2: 8, real 2x2: 4, table lookups: 4), halved per control.  Passes without a
+        register-stage form are not counted."""
+        n = self.n_local if n_local is None else n_local
+        per = {_abi.QLS_RS_G1: (8, 4), _abi.QLS_RS_G2: (16, 8), _abi.QLS_RS_DIAG: (4, 4), _abi.QLS_RS_MUXRY: (4, 4)}
+        tot = 0.0
+        for o in range(self.n_rs_ops):
+            op = self.rs_ops[o]
+            if op.kind not in per:
+                continue
+            c = per[op.kind][1 if (op.flags & _abi.QLS_OP_FLAG_REAL) else 0]
+            nc = bin(op.xc_mask).count("1") + bin(op.ctl_tmask).count("1") + bin(op.ctl_rmask).count("1")
+            tot += c * 0.5**nc * 2.0**n
+        return tot
+
     def amp_updates(self) -> int:
         """Sum over fused blocks of ``2**(n-c)``."""
         tot = 0

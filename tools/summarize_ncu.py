@@ -61,8 +61,34 @@ def report(path):
             print(f"| `{w}` | {units[i]} | " + " | ".join(r[i] for r in rows[2:]) + " |")
 
 
+def traffic(path, algorithmic_bytes_per_launch, out_json, note):
+    """profiles/traffic.json: measured DRAM bytes per algorithmic byte of the captured launches."""
+    import json
+
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    tot = []
+    for r in rows[2:]:
+        b = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            b += float(r[i].replace(",", "")) * scale[units[i]]
+        tot.append(b)
+    ratio = sum(tot) / (len(tot) * algorithmic_bytes_per_launch)
+    doc = {"dram_bytes_per_algorithmic_byte": ratio, "dram_bytes_per_launch": tot,
+           "algorithmic_bytes_per_launch": algorithmic_bytes_per_launch,
+           "source": f"ncu --set full, {len(tot)} launches of qls_rs_pass_kernel, {note} ({path.split('/')[-1]})"}
+    with open(out_json, "w") as fh:
+        json.dump(doc, fh, indent=1)
+    print(json.dumps(doc))
+
+
 if __name__ == "__main__":
-    if sys.argv[1].endswith(".csv"):
+    if sys.argv[1] == "--traffic":  # --traffic report.ncu-rep <algorithmic bytes per launch> out.json "note"
+        traffic(sys.argv[2], float(sys.argv[3]), sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "")
+    elif sys.argv[1].endswith(".csv"):
         launches(sys.argv[1])
     else:
         report(sys.argv[1])
