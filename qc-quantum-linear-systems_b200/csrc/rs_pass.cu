@@ -57,18 +57,19 @@ struct RsStep {
   uint16_t moff;  // G1/G2: matrix offset in the image body, in 16-byte units
 };
 
-enum {
-  RS_C_LOAD_D = 1,   // global -> registers (lanes are the low tile bits)
-  RS_C_LOAD_S = 2,   // global -> shared (cp.async) -> registers
-  RS_C_TRANS = 3,    // registers -> shared -> registers in the next stage's layout
-  RS_C_STORE_D = 4,  // registers -> global; ends the tile
-  RS_C_STORE_S = 5,  // registers -> shared -> global; ends the tile
-  RS_C_DIAG = 6,     // table indexed by register qubits and/or controlled inside the tile
-  RS_C_DIAG1 = 7,    // one phase per thread
-  RS_C_MUX = 8,      // + register qubit
-  RS_C_G1 = 16,      // + 4 * register qubit + 2 * real + ctl
-  RS_C_G2 = 64,      // + 4 * pair + 2 * real + ctl
-  RS_C_ACQ = 15      // take the SM's FP64 token (two-group kernels): a run of heavy ops follows
+enum {  // dense numbering: the step switch compiles to one jump table
+  RS_C_LOAD_D = 0,   // global -> registers (lanes are the low tile bits)
+  RS_C_LOAD_S = 1,   // global -> shared (cp.async) -> registers
+  RS_C_TRANS = 2,    // registers -> shared -> registers in the next stage's layout
+  RS_C_STORE_D = 3,  // registers -> global; ends the tile
+  RS_C_STORE_S = 4,  // registers -> shared -> global; ends the tile
+  RS_C_ACQ = 5,      // take the SM's FP64 token (two-group kernels): a run of heavy ops follows
+  RS_C_DIAG = 6,     // table indexed by register qubits, no control inside the tile
+  RS_C_DIAGC = 7,    // ... with a control inside the tile
+  RS_C_DIAG1 = 8,    // one phase per thread
+  RS_C_MUX = 9,      // + register qubit (0..4)
+  RS_C_G1 = 14,      // + 4 * register qubit + 2 * real + ctl
+  RS_C_G2 = 34       // + 4 * pair + 2 * real + ctl
 };
 constexpr uint16_t RS_F_RELEASE = 1;  // RsStep.moff of TRANS / STORE_*: hand the FP64 token back first
 constexpr uint16_t RS_IDLE = 0xFFFFu;
@@ -192,7 +193,7 @@ __device__ __forceinline__ void rs_diag1(V (&a)[A], const V* __restrict__ table,
   for (int r = 0; r < A; ++r) a[r] = cmul(a[r], ph);
 }
 
-template <typename V, int A, int KR>
+template <typename V, int A, int KR, bool CTL>
 __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
   uint32_t d[KR];
 #pragma unroll
@@ -207,7 +208,7 @@ __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* _
     for (int r = 0; r < CH; ++r) ph[r] = __ldg(tb + rs_tidx<KR>(0u, d, c + r));  // index is valid whatever the controls say
 #pragma unroll
     for (int r = 0; r < CH; ++r)
-      if (tok && (((uint32_t)(c + r) & rm) == rv)) a[c + r] = cmul(a[c + r], ph[r]);
+      if (!CTL || (tok && (((uint32_t)(c + r) & rm) == rv))) a[c + r] = cmul(a[c + r], ph[r]);
   }
 }
 
@@ -247,6 +248,9 @@ __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* 
   }
 }
 
+// tile-local bit (lq) and swizzled shared-memory offset (cq) of each register qubit of a stage.
+// (Reading them precomputed from the record's rt[] makes ptxas drop the uniform datapath for the whole
+// step loop -- measured with the DFMA.*UR count -- so they are recomputed: a dozen uniform ALU ops.)
 template <int KR, int SH>
 __device__ __forceinline__ void rs_stage_bits(const QlsRsOp& sp, uint32_t (&cq)[KR], uint32_t (&lq)[KR]) {
 #pragma unroll
@@ -340,9 +344,12 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
       ++s;
       const QlsRsOp& op = recs[st.rec];
       const V* M = reinterpret_cast<const V*>(c_img.body + 16u * st.moff);
+#ifdef QLS_RS_TIMING  // timing experiments only (profiles/README.md): switch parts of the kernel off
       const bool skip = KR == 4 && sizeof(V) == 16 && dbg != 0 && (((dbg & 1u) && st.code >= RS_C_G1) || ((dbg & 2u) && st.code == RS_C_TRANS) ||
-                                    ((dbg & 4u) && st.code >= RS_C_DIAG && st.code < RS_C_G1));  // timing experiments only
-      if (!__any_sync(0xffffffffu, skip)) switch (st.code) {
+                                    ((dbg & 4u) && st.code >= RS_C_DIAG && st.code < RS_C_G1));
+      if (!__any_sync(0xffffffffu, skip))
+#endif
+      switch (st.code) {
         case RS_C_LOAD_D: {
           // all register qubits sit above the 5 lane bits: every warp load is 512 contiguous bytes
           uint32_t cq[KR], lq[KR];
@@ -431,12 +438,13 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           break;
         }
         case RS_C_DIAG:
+        case RS_C_DIAGC:
         case RS_C_DIAG1: {
-          const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;
           const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
           const V* table = reinterpret_cast<const V*>(pool + op.pool_off);
-          if (st.code == RS_C_DIAG1) rs_diag1<V, A>(a, table, ti0, tok);
-          else rs_diag<V, A, KR>(a, op, table, ti0, tok);
+          if (st.code == RS_C_DIAG) rs_diag<V, A, KR, false>(a, op, table, ti0, true);
+          else if (st.code == RS_C_DIAGC) rs_diag<V, A, KR, true>(a, op, table, ti0, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval);
+          else rs_diag1<V, A>(a, table, ti0, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval);
           break;
         }
 #define QLS_MUX_CASE(q)                                                                                              \
@@ -617,7 +625,7 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
       } else {
         bool reg_bits = op.ctl_rmask != 0;
         for (int j = 0; j < KR; ++j) reg_bits |= op.rt[1 << j] != 0;
-        code[o] = reg_bits ? RS_C_DIAG : RS_C_DIAG1;
+        code[o] = !reg_bits ? RS_C_DIAG1 : (ctl ? RS_C_DIAGC : RS_C_DIAG);
       }
     }
     if (!ok || __builtin_popcountll(cmask) > RS_MAX_CBITS) continue;
