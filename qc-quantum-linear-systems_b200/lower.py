@@ -420,6 +420,7 @@ class PassInfo:
     op_controls: List[int]
     heavy: bool
     rs_stages: int = 0  # > 0: the pass also has a register-stage form with this many stages
+    touched_fraction: float = 1.0  # tiles on which at least one op fires (the register-stage kernel skips the rest)
 
 
 @dataclass
@@ -448,7 +449,8 @@ class LoweredProgram:
         """Algorithmic HBM bytes of pass ``i``: one read + one write of every touched amplitude
         (``2*S*2**(n-c)``)."""
         n = self.n_local if n_local is None else n_local
-        return 2 * self.amp_bytes() * 2 ** (n - self.pass_info[i].fixed_bits)
+        pi = self.pass_info[i]
+        return int(2 * self.amp_bytes() * 2 ** (n - pi.fixed_bits) * pi.touched_fraction)
 
     def total_pass_bytes(self) -> int:
         return sum(self.pass_bytes(i) for i in range(self.n_passes))
@@ -708,7 +710,21 @@ class _Emitter:
             p.fseg[j].src, p.fseg[j].width, p.fseg[j].dst = src, w, dst
         idx = len(self.passes)
         self.passes.append(p)
-        self.pass_info.append(PassInfo(T, L, high_sorted, len(common), p.op_count, n_source, op_controls, heavy, rs_stages))
+        touched = 1.0
+        if rs_stages:
+            # controls outside the tile: a tile whose control qubits switch every op off is skipped by the kernel
+            recs = [r for r in self.rs_ops[rs_begin:] if r.kind != _abi.QLS_RS_STAGE]
+            cmask = 0
+            for r in recs:
+                cmask |= r.xc_mask & ~fix_mask
+            cb = [q for q in range(64) if (cmask >> q) & 1]
+            if recs and all(r.xc_mask & ~fix_mask for r in recs) and len(cb) <= self.MAX_EXT_CONTROLS:
+                live = 0
+                for v in range(2 ** len(cb)):
+                    a = sum(((v >> j) & 1) << q for j, q in enumerate(cb))
+                    live += any((a & r.xc_mask & ~fix_mask) == (r.xc_val & ~fix_mask) for r in recs)
+                touched = live / 2 ** len(cb)
+        self.pass_info.append(PassInfo(T, L, high_sorted, len(common), p.op_count, n_source, op_controls, heavy, rs_stages, touched))
         if self.steps and self.steps[-1].kind == "passes" and self.steps[-1].pass_end == idx:
             self.steps[-1].pass_end = idx + 1
         else:
@@ -756,7 +772,11 @@ class _Emitter:
                 regq_sorted = sorted(regq)
                 rho = {p_: j for j, p_ in enumerate(regq_sorted)}
                 tpos = [p_ for p_ in range(T) if p_ not in regq]
-                direct = min(regq_sorted) >= 5
+                # global <-> register access without shared-memory staging: the lanes are the five lowest
+                # non-register tile bits; every 32-byte sector (64 bytes with bit 1) of a warp access is fully
+                # used as long as the lowest tile bits are lane bits, whatever the higher register qubits are
+                low_lane_bits = 2 if self.opts.dtype == "fp64" else 3
+                direct = min(regq_sorted) >= low_lane_bits
                 if not direct and self.opts.dtype == "fp64":
                     tpos = self._conflict_free_lanes(tpos)
                 tbit = {p_: j for j, p_ in enumerate(tpos)}
