@@ -378,6 +378,65 @@ def test_register_stage_kernel_hhl_shaped_many_tiles(cuda_device):
     assert _fidelity(got, want) >= FID
 
 
+def _controlled_chain_circuit(n, n_ctl, rng, always_controlled):
+    """2-qubit unitaries and diagonals on the twelve low qubits (all five non-contiguous tile slots
+    are used up by qubits 7..11), each controlled by one of ``n_ctl`` high qubits: the controls are
+    OUTSIDE the 12-bit tile, i.e. they select the step-list variant in csrc/rs_pass.cu.  More than 6
+    distinct ones force the lowering to split the pass; without unconditional ops a tile whose
+    controls are all off is idle (neither read nor written)."""
+    from qls_b200.circuit import Gate, QuantumCircuit
+
+    qc = QuantumCircuit(n, name="ctl_chain")
+    low = 12
+    for q in range(low if always_controlled else 0, n):
+        qc.h(q)
+    for j in range(3 * n_ctl):
+        c = n - 1 - (j % n_ctl)
+        a = 7 + j % 5  # every one of 7..11 is touched
+        b = int(rng.integers(0, 7))
+        qc.append(Gate("unitary", 2, [], random_unitary(2, rng)).control(1, int(rng.integers(2))), [c, a, b])
+        if j % 3 == 0:
+            d = Gate("diagonal", 2, [], np.diag(np.exp(1j * rng.uniform(-3, 3, 4)))).control(1)
+            qc.append(d, [c, a, b])
+        if not always_controlled and j % 5 == 4:
+            qc.unitary(random_unitary(2, rng), [a, b])
+    return qc
+
+
+@pytest.mark.parametrize("n_ctl,always", [(3, True), (5, False), (8, True), (8, False)])
+def test_register_stage_variants_external_controls(cuda_device, n_ctl, always):
+    """Step-list variants: idle tiles (every op controlled), > 6 control qubits (pass split)."""
+    from qls_b200.lower import LoweringOptions, lower_circuit
+    from qls_b200.statevector import Statevector
+
+    rng = np.random.default_rng(9100 + n_ctl + always)
+    n = 21
+    qc = _controlled_chain_circuit(n, n_ctl, rng, always)
+    low = lower_circuit(qc, LoweringOptions(dtype="fp64"))
+    assert any(p.rs_stages > 0 for p in low.pass_info)
+    if always and n_ctl == 8:
+        assert any(p.touched_fraction < 1.0 for p in low.pass_info)  # idle tiles exist
+    if n_ctl > 6:
+        assert low.n_passes >= 5  # split by the cap on control qubits outside the tile
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = Statevector(qc).data
+    assert np.max(np.abs(got - want)) <= TOL64
+    assert _fidelity(got, want) >= FID
+
+
+def test_register_stage_small_tiles(cuda_device):
+    """2^11-amplitude tiles (128 threads, four CTAs per SM): the other fp64 instantiation of the kernel."""
+    from qls_b200.lower import LoweringOptions
+    from qls_b200.statevector import Statevector
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    n = 19
+    qc = hhl_shaped_circuit(n)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = Statevector(qc, options=LoweringOptions(dtype="fp64", tile_bits=11)).data
+    assert np.max(np.abs(got - want)) <= TOL64
+
+
 # ---- edge cases ------------------------------------------------------------------------------------
 
 
