@@ -67,9 +67,11 @@ enum {  // dense numbering: the step switch compiles to one jump table
   RS_C_DIAG = 6,     // table indexed by register qubits, no control inside the tile
   RS_C_DIAGC = 7,    // ... with a control inside the tile
   RS_C_DIAG1 = 8,    // one phase per thread
-  RS_C_MUX = 9,      // + register qubit (0..4)
-  RS_C_G1 = 14,      // + 4 * register qubit + 2 * real + ctl
-  RS_C_G2 = 34       // + 4 * pair + 2 * real + ctl
+  RS_C_DIAGW = 9,    // table index is the same for all lanes of a warp: the entries are fetched once per warp
+  RS_C_DIAGWC = 10,  // ... controlled by register qubits
+  RS_C_MUX = 11,     // + register qubit (0..4)
+  RS_C_G1 = 16,      // + 4 * register qubit + 2 * real + ctl
+  RS_C_G2 = 36       // + 4 * pair + 2 * real + ctl
 };
 constexpr uint16_t RS_F_RELEASE = 1;  // RsStep.moff of TRANS / STORE_*: hand the FP64 token back first
 constexpr uint16_t RS_IDLE = 0xFFFFu;
@@ -212,6 +214,32 @@ __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* _
   }
 }
 
+// Table whose index does not depend on the lane (QFT phase ladders on the clock register while the
+// lanes are data qubits): the warp needs only the 2^KR entries of its register combinations.  Lane r
+// fetches entry r, the warp shares them through a 2^KR-entry scratch line in shared memory
+// (broadcast reads), instead of every lane loading all of them.
+// CTL: control on register qubits only (warp-uniform predicate; a per-thread predicate between the two
+// warp barriers makes ptxas give up the uniform datapath for the whole step loop).
+template <typename V, int A, int KR, bool CTL>
+__device__ __forceinline__ void rs_diagw(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0,
+                                         V* __restrict__ scr, int lane) {
+  {  // every lane takes part (lanes >= A duplicate entry lane % A): no divergent branch in the step loop
+    const int e = lane & (A - 1);
+    uint32_t t = ti0;
+#pragma unroll
+    for (int j = 0; j < KR; ++j) t |= ((e >> j) & 1) ? (uint32_t)op.rt[1 << j] : 0u;
+    scr[e] = __ldg(&table[t]);
+  }
+  __syncwarp();
+  const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
+#pragma unroll
+  for (int r = 0; r < A; ++r) {
+    const V ph = scr[r];
+    if (!CTL || (((uint32_t)r & rm) == rv)) a[r] = cmul(a[r], ph);
+  }
+  __syncwarp();  // the scratch line is free for the next table
+}
+
 template <typename V, int A, int KR, int RQ>
 __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
   uint32_t d[KR];
@@ -304,7 +332,9 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
   V* sm = reinterpret_cast<V*>(smem_raw + (size_t)grp * TILE_BYTES);
   uint4* sm16 = reinterpret_cast<uint4*>(smem_raw + (size_t)grp * TILE_BYTES);
   uint64_t* hoff = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GROUPS * TILE_BYTES);  // [1 << n_high]
-  uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + (1 << c_img.h.n_high));  // [stages][RS_THREADS]
+  uint16_t* ptb = reinterpret_cast<uint16_t*>(hoff + ((1 << c_img.h.n_high) | 1) + 1);  // [stages][RS_THREADS]; even entry count: 16-byte aligned
+  // per-warp scratch line of A table entries (RS_C_DIAGW), behind ptb (16-byte aligned: ptb rows are 2 * RS_THREADS bytes)
+  V* wscr = reinterpret_cast<V*>(ptb + (size_t)c_img.h.n_stages * RS_THREADS) + (threadIdx.x >> 5) * A;
 #define RS_SYNC() do { if (GROUPS == 1) __syncthreads(); else rs_group_sync<1>(grp, RS_THREADS); } while (0)
 
   const QlsRsOp* recs = reinterpret_cast<const QlsRsOp*>(c_img.body);
@@ -358,7 +388,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
 #pragma unroll
           for (int r = 0; r < A; ++r) {
             const uint32_t idx = rs_addr<KR>(ltb, lq, r);
-            a[r] = __ldcs(&state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]]);  // streaming: keep L1 for the tables
+            a[r] = __ldcg(&state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]]);  // L2 only: L1 is kept for the phase tables
           }
           break;
         }
@@ -407,7 +437,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
 #pragma unroll
           for (int r = 0; r < A; ++r) {
             const uint32_t idx = rs_addr<KR>(ltb, lq, r);
-            __stcs(&state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]], a[r]);
+            __stcg(&state[base | (uint64_t)(idx & ((1u << L) - 1u)) | hoff[idx >> L]], a[r]);
           }
           break;
         }
@@ -424,7 +454,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           for (int u = tid; u < UNITS; u += RS_THREADS) {
             const int i = u * APU;
             const uint64_t g = base | (uint64_t)(i & ((1 << L) - 1)) | hoff[i >> L];
-            __stcs(reinterpret_cast<uint4*>(&state[g]), sm16[swz<SH>((uint32_t)i) >> SH]);
+            __stcg(reinterpret_cast<uint4*>(&state[g]), sm16[swz<SH>((uint32_t)i) >> SH]);
           }
           break;
         }
@@ -435,6 +465,13 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
             }
             RS_SYNC();
           }
+          break;
+        }
+        case RS_C_DIAGW:
+        case RS_C_DIAGWC: {
+          const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
+          const V* table = reinterpret_cast<const V*>(pool + op.pool_off);
+          rs_diagw<V, A, KR, true>(a, op, table, ti0, wscr, tid & 31);  // one instantiation: (r & 0) == 0 without a control
           break;
         }
         case RS_C_DIAG:
@@ -519,7 +556,8 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
   QLS_ARG(free_bits >= 0 && free_bits < 40, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
   const uint64_t n_tiles = 1ull << free_bits;
   const int n_stages = p.pad >> 8;  // counted by qls_program_create
-  const size_t smem = ((size_t)GROUPS * sizeof(V) << T) + (sizeof(uint64_t) << p.n_high) + (size_t)n_stages * RS_THREADS * sizeof(uint16_t);
+  const size_t smem = ((size_t)GROUPS * sizeof(V) << T) + sizeof(uint64_t) * (((1u << p.n_high) | 1u) + 1u) + (size_t)n_stages * RS_THREADS * sizeof(uint16_t) +
+                      (size_t)(GROUPS * RS_THREADS / 32) * (sizeof(V) << KR);
   QLS_ARG(smem <= (size_t)(224 / CTAS) * 1024, "register-stage pass needs %zu bytes of shared memory", smem);
   auto kern = qls_rs_pass_kernel<R, T, KR, CTAS, GROUPS>;
   static bool attr_set[64] = {false};
@@ -625,7 +663,10 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
       } else {
         bool reg_bits = op.ctl_rmask != 0;
         for (int j = 0; j < KR; ++j) reg_bits |= op.rt[1 << j] != 0;
-        code[o] = !reg_bits ? RS_C_DIAG1 : (ctl ? RS_C_DIAGC : RS_C_DIAG);
+        bool lane_free = true;  // no lane bit (thread bits 0..4) in the table index
+        for (int j = 0; j < op.n_tseg; ++j) lane_free &= op.tseg[j].src >= 5;
+        if (op.ctl_tmask) lane_free = false;  // the warp-shared form takes register-qubit controls only
+        code[o] = !reg_bits ? RS_C_DIAG1 : lane_free ? (ctl ? RS_C_DIAGWC : RS_C_DIAGW) : (ctl ? RS_C_DIAGC : RS_C_DIAG);
       }
     }
     if (!ok || __builtin_popcountll(cmask) > RS_MAX_CBITS) continue;
