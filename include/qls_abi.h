@@ -204,6 +204,14 @@ int qls_pack_bit(const void* state, void* buffer, int n_local, int dtype, int qu
                  uint64_t chunk_count, void* stream);
 int qls_unpack_bit(void* state, const void* buffer, int n_local, int dtype, int qubit, int bit_value, uint64_t chunk_begin,
                    uint64_t chunk_count, void* stream);
+/* The same for k local bits at once (qubits_host: ascending positions; bit m of value_bits is the value
+ * of qubits_host[m]; count = 2^(n_local-k) per sub-block): a k-qubit remap exchanges 2^k - 1 such
+ * sub-blocks, one with every rank that differs in the k global bits, instead of k half-shard swaps. */
+#define QLS_MAX_REMAP_BITS 6
+int qls_pack_bits(const void* state, void* buffer, int n_local, int dtype, const int* qubits_host, int k, uint64_t value_bits,
+                  uint64_t chunk_begin, uint64_t chunk_count, void* stream);
+int qls_unpack_bits(void* state, const void* buffer, int n_local, int dtype, const int* qubits_host, int k, uint64_t value_bits,
+                    uint64_t chunk_begin, uint64_t chunk_count, void* stream);
 
 #ifdef __cplusplus
 }

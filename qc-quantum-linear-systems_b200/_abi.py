@@ -116,6 +116,8 @@ SYMBOLS = {
     "qls_batch_expect_z": (_i, [_vp, _u32, _i, _i, _vp, _u32, _u32, _vp, _vp]),
     "qls_pack_bit": (_i, [_vp, _vp, _i, _i, _i, _i, _u64, _u64, _vp]),
     "qls_unpack_bit": (_i, [_vp, _vp, _i, _i, _i, _i, _u64, _u64, _vp]),
+    "qls_pack_bits": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _vp]),
+    "qls_unpack_bits": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

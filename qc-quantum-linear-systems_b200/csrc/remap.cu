@@ -47,3 +47,66 @@ extern "C" int qls_unpack_bit(void* state, const void* buffer, int n_local, int 
                               uint64_t chunk_begin, uint64_t chunk_count, void* stream) {
   return pack_impl<false>(state, const_cast<void*>(buffer), n_local, dtype, qubit, bit_value, chunk_begin, chunk_count, stream);
 }
+
+// ---- several bits at once (k-qubit remap = one all-to-all instead of k pairwise half-shard swaps) -----
+
+struct QlsBitSet {
+  int k;
+  int pos[QLS_MAX_REMAP_BITS];  // ascending local bit positions
+  uint64_t value;               // OR of (bit value << position)
+};
+
+// element j of the sub-block (j in [0, 2^(n-k))) sits at deposit(j) | value: j with a zero bit
+// inserted at every position of the set
+template <typename V, bool PACK>
+__global__ void __launch_bounds__(256) qls_pack_bits_kernel(V* __restrict__ state, V* __restrict__ buffer, const QlsBitSet bs,
+                                                             uint64_t begin, uint64_t count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+    uint64_t i = begin + t;
+#pragma unroll
+    for (int m = 0; m < QLS_MAX_REMAP_BITS; ++m)
+      if (m < bs.k) i = ((i >> bs.pos[m]) << (bs.pos[m] + 1)) | (i & ((1ull << bs.pos[m]) - 1ull));
+    i |= bs.value;
+    if (PACK) buffer[t] = state[i];
+    else state[i] = buffer[t];
+  }
+}
+
+template <bool PACK>
+static int pack_bits_impl(void* state, void* buffer, int n_local, int dtype, const int* qubits, int k, uint64_t value_bits,
+                          uint64_t begin, uint64_t count, void* stream) {
+  QLS_ARG(state && buffer && qubits, "null pointer");
+  QLS_ARG(k >= 1 && k <= QLS_MAX_REMAP_BITS && k <= n_local, "bad bit count %d", k);
+  QlsBitSet bs;
+  bs.k = k;
+  bs.value = 0;
+  for (int m = 0; m < k; ++m) {
+    QLS_ARG(qubits[m] >= 0 && qubits[m] < n_local && (m == 0 || qubits[m] > qubits[m - 1]), "bit positions must be ascending and local");
+    bs.pos[m] = qubits[m];
+    bs.value |= ((value_bits >> m) & 1ull) << qubits[m];
+  }
+  for (int m = k; m < QLS_MAX_REMAP_BITS; ++m) bs.pos[m] = 0;
+  QLS_ARG(begin + count <= (1ull << (n_local - k)), "chunk outside the sub-block");
+  if (count == 0) return QLS_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint64_t want = (count + 255) / 256;
+  unsigned grid = (unsigned)(want > 148ull * 16 ? 148 * 16 : want);
+  if (dtype == QLS_C128)
+    qls_pack_bits_kernel<double2, PACK><<<grid, 256, 0, s>>>(reinterpret_cast<double2*>(state), reinterpret_cast<double2*>(buffer), bs,
+                                                             begin, count);
+  else
+    qls_pack_bits_kernel<float2, PACK><<<grid, 256, 0, s>>>(reinterpret_cast<float2*>(state), reinterpret_cast<float2*>(buffer), bs,
+                                                            begin, count);
+  QLS_CUDA(cudaGetLastError());
+  return QLS_OK;
+}
+
+extern "C" int qls_pack_bits(const void* state, void* buffer, int n_local, int dtype, const int* qubits, int k,
+                             uint64_t value_bits, uint64_t chunk_begin, uint64_t chunk_count, void* stream) {
+  return pack_bits_impl<true>(const_cast<void*>(state), buffer, n_local, dtype, qubits, k, value_bits, chunk_begin, chunk_count, stream);
+}
+extern "C" int qls_unpack_bits(void* state, const void* buffer, int n_local, int dtype, const int* qubits, int k,
+                               uint64_t value_bits, uint64_t chunk_begin, uint64_t chunk_count, void* stream) {
+  return pack_bits_impl<false>(state, const_cast<void*>(buffer), n_local, dtype, qubits, k, value_bits, chunk_begin, chunk_count, stream);
+}

@@ -167,9 +167,10 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
 class ShardedRunner:
     """Drives one rank's shard through a plan.  ``engine`` supplies the local work:
 
-    ``run_local(lowered, initialise)``; ``pack(local_pos, bit, begin, count) -> tensor`` (a view of
-    engine-owned scratch); ``unpack(tensor, local_pos, bit, begin, count)``; ``recv_buffer(count)``;
-    ``half`` (amplitudes per slab = 2**(n_local-1))."""
+    ``run_local(lowered, initialise)``; ``pack(local_positions, value_bits, begin, count) -> tensor``
+    (a view of engine-owned scratch: the sub-block whose local bits ``local_positions[m]`` equal bit
+    ``m`` of ``value_bits``); ``unpack(tensor, local_positions, value_bits, begin, count)``;
+    ``recv_buffer(count)``."""
 
     def __init__(self, plan: ShardedPlan, engine: Any, rank: int, world: int, chunk_amps: int = 1 << 26, dist: Any = None):
         self.plan, self.engine, self.rank, self.world = plan, engine, rank, world
@@ -188,40 +189,51 @@ class ShardedRunner:
             else:
                 if first:
                     raise ValueError("a plan cannot start with a remap")
-                for gpos, lpos in seg.pairs:
-                    self.swap(gpos - self.plan.n_local, lpos)
+                self.swap_many([(gpos - self.plan.n_local, lpos) for gpos, lpos in seg.pairs])
 
-    def swap(self, gbit: int, lpos: int) -> None:
-        """Exchange global position ``n_local + gbit`` with local position ``lpos``.
+    def swap_many(self, pairs: Sequence[Tuple[int, int]]) -> None:
+        """Exchange the global positions ``n_local + gbit`` with the local positions ``lpos`` of all
+        ``k`` pairs at once: the amplitude at (global bits r, local bits v) moves to (global bits v,
+        local bits r).  Every rank keeps the sub-block whose local bits equal its own global bits and
+        swaps the sub-block with local bits ``p`` with the rank whose global bits are ``p``, in place:
+        2^k - 1 pairwise exchanges of 2^(n_local-k) amplitudes = (1 - 2^-k) of a shard on the wire,
+        instead of k/2 with one half-shard swap per qubit.  The rounds use the same XOR offset on all
+        ranks, so they form perfect matchings (no ordering deadlock).
 
         Software pipeline over chunks with two scratch slots: while chunk ``i`` is on the wire,
-        chunk ``i+1`` is packed and chunk ``i-1`` is unpacked (the exchange depends only on its own
-        pack; NCCL runs on its own stream)."""
+        chunk ``i+1`` is packed and chunk ``i-1`` is unpacked (NCCL runs on its own stream)."""
         dist = self.dist
-        partner = self.rank ^ (1 << gbit)
-        mine = (self.rank >> gbit) & 1
-        send_bit = 1 - mine  # the slab whose local bit differs from my rank bit moves
-        half = self.engine.half
-        chunks = [(b, min(self.chunk, half - b)) for b in range(0, half, self.chunk)]
+        order = sorted(range(len(pairs)), key=lambda j: pairs[j][1])  # local positions ascending
+        gbits = [pairs[j][0] for j in order]
+        lposs = [pairs[j][1] for j in order]
+        k = len(pairs)
+        block = 2 ** (self.plan.n_local - k)
+        chunks = [(b, min(self.chunk, block - b)) for b in range(0, block, self.chunk)]
+        for d in range(1, 2**k):
+            partner = self.rank
+            for j in range(k):
+                if (d >> j) & 1:
+                    partner ^= 1 << gbits[j]
+            value = sum(((partner >> gbits[j]) & 1) << j for j in range(k))  # partner's global bits, as local-bit values
 
-        def start(i: int):
-            begin, count = chunks[i]
-            out = self.engine.pack(lpos, send_bit, begin, count, slot=i & 1)
-            inc = self.engine.recv_buffer(count, slot=i & 1)
-            ops = [dist.P2POp(dist.isend, out, partner), dist.P2POp(dist.irecv, inc, partner)]
-            if self.rank > partner:
-                ops.reverse()
-            self.bytes_sent += out.numel() * out.element_size()
-            return dist.batch_isend_irecv(ops), inc
+            def start(i: int):
+                begin, count = chunks[i]
+                out = self.engine.pack(lposs, value, begin, count, slot=i & 1)
+                inc = self.engine.recv_buffer(count, slot=i & 1)
+                ops = [dist.P2POp(dist.isend, out, partner), dist.P2POp(dist.irecv, inc, partner)]
+                if self.rank > partner:
+                    ops.reverse()
+                self.bytes_sent += out.numel() * out.element_size()
+                return dist.batch_isend_irecv(ops), inc
 
-        inflight = start(0)
-        for i, (begin, count) in enumerate(chunks):
-            nxt = start(i + 1) if i + 1 < len(chunks) else None
-            reqs, inc = inflight
-            for req in reqs:
-                req.wait()
-            self.engine.unpack(inc, lpos, send_bit, begin, count)
-            inflight = nxt
+            inflight = start(0)
+            for i, (begin, count) in enumerate(chunks):
+                nxt = start(i + 1) if i + 1 < len(chunks) else None
+                reqs, inc = inflight
+                for req in reqs:
+                    req.wait()
+                self.engine.unpack(inc, lposs, value, begin, count)
+                inflight = nxt
 
 
 class CudaShardEngine:
@@ -255,21 +267,27 @@ class CudaShardEngine:
     def run_local(self, lowered: LoweredProgram, initialise: bool) -> None:
         self.programs[id(lowered)].run(self.state, initialise=initialise)
 
-    def pack(self, lpos: int, bit: int, begin: int, count: int, slot: int = 0):
+    def pack(self, lposs: Sequence[int], value: int, begin: int, count: int, slot: int = 0):
+        import ctypes as C
+
         st = self.state
+        arr = (C.c_int * len(lposs))(*lposs)
         with self.torch.cuda.device(st.device):
-            self._abi.check(st.lib.qls_pack_bit(st.ptr, self._send[slot].data_ptr(), st.n_local, st.abi_dtype, lpos, bit, begin,
-                                                count, self._stream()))
+            self._abi.check(st.lib.qls_pack_bits(st.ptr, self._send[slot].data_ptr(), st.n_local, st.abi_dtype, arr, len(lposs),
+                                                 value, begin, count, self._stream()))
         return self._send[slot][:count]
 
     def recv_buffer(self, count: int, slot: int = 0):
         return self._recv[slot][:count]
 
-    def unpack(self, buf, lpos: int, bit: int, begin: int, count: int) -> None:
+    def unpack(self, buf, lposs: Sequence[int], value: int, begin: int, count: int) -> None:
+        import ctypes as C
+
         st = self.state
+        arr = (C.c_int * len(lposs))(*lposs)
         with self.torch.cuda.device(st.device):
-            self._abi.check(st.lib.qls_unpack_bit(st.ptr, buf.data_ptr(), st.n_local, st.abi_dtype, lpos, bit, begin, count,
-                                                  self._stream()))
+            self._abi.check(st.lib.qls_unpack_bits(st.ptr, buf.data_ptr(), st.n_local, st.abi_dtype, arr, len(lposs), value, begin,
+                                                   count, self._stream()))
 
 
 class ShardedShapedSolver:
@@ -317,8 +335,7 @@ class ShardedShapedSolver:
             if seg.kind == "local":
                 self.engine.programs[id(seg.lowered)].run(self.state, initialise=False)  # state prepared by _prepare
             else:
-                for gpos, lpos in seg.pairs:
-                    self.runner.swap(gpos - self.plan.n_local, lpos)
+                self.runner.swap_many([(gpos - self.plan.n_local, lpos) for gpos, lpos in seg.pairs])
 
     def run_device(self, b_device=None) -> None:
         self._prepare(b_device=b_device)
@@ -375,7 +392,10 @@ class ShardedShapedSolver:
             "source_gates": self.plan.n_source_gates,
             "pass_bytes_per_gpu": sum(l.total_pass_bytes() for l in local),
             "remaps": self.plan.n_swaps,
-            "remap_bytes_sent_per_gpu": self.plan.n_swaps * self.engine.half * self.lowered.amp_bytes(),
+            "remap_exchanges": sum(1 for s in self.plan.segments if s.kind == "swap"),
+            # a k-qubit exchange puts (1 - 2^-k) of the shard on the wire
+            "remap_bytes_sent_per_gpu": sum(int((1 - 0.5 ** len(s.pairs)) * 2 * self.engine.half) * self.lowered.amp_bytes()
+                                            for s in self.plan.segments if s.kind == "swap"),
         }
 
     def time_passes(self, repeats: int = 1):
@@ -394,8 +414,7 @@ class ShardedShapedSolver:
                 else:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    for gpos, lpos in seg.pairs:
-                        self.runner.swap(gpos - self.plan.n_local, lpos)
+                    self.runner.swap_many([(gpos - self.plan.n_local, lpos) for gpos, lpos in seg.pairs])
                     e1.record()
                     torch.cuda.synchronize()
                     remap += e0.elapsed_time(e1)

@@ -50,18 +50,24 @@ class NumpyShardEngine:
             for pi in range(s.pass_begin, s.pass_end):
                 run_pass(self.state, lowered.passes[pi], lowered.ops, pool, np.complex128, self.n_local, self.index_offset)
 
-    def _slab_index(self, lpos, bit, begin, count):
-        j = np.arange(begin, begin + count, dtype=np.int64)
-        return ((j >> lpos) << (lpos + 1)) | (bit << lpos) | (j & ((1 << lpos) - 1))
+    def _block_index(self, lposs, value, begin, count):
+        """Indices of the sub-block whose local bits lposs[m] (ascending) equal bit m of value."""
+        i = np.arange(begin, begin + count, dtype=np.int64)
+        for m, p in enumerate(lposs):
+            assert m == 0 or p > lposs[m - 1]
+            i = ((i >> p) << (p + 1)) | (i & ((1 << p) - 1))
+        for m, p in enumerate(lposs):
+            i |= ((value >> m) & 1) << p
+        return i
 
-    def pack(self, lpos, bit, begin, count, slot=0):
-        return self.torch.from_numpy(self.state[self._slab_index(lpos, bit, begin, count)].copy())
+    def pack(self, lposs, value, begin, count, slot=0):
+        return self.torch.from_numpy(self.state[self._block_index(lposs, value, begin, count)].copy())
 
     def recv_buffer(self, count, slot=0):
         return self.torch.empty(count, dtype=self.torch.complex128)
 
-    def unpack(self, buf, lpos, bit, begin, count):
-        self.state[self._slab_index(lpos, bit, begin, count)] = buf.numpy()
+    def unpack(self, buf, lposs, value, begin, count):
+        self.state[self._block_index(lposs, value, begin, count)] = buf.numpy()
 
 
 def _logical_state(plan, shards):
@@ -112,18 +118,27 @@ def _run_fake(plan, world, chunk):
                 e.run_local(seg.lowered, initialise=first)
             first = False
             continue
-        for gpos, lpos in seg.pairs:
-            gbit = gpos - plan.n_local
-            half = engines[0].half
-            for begin in range(0, half, chunk):
-                count = min(chunk, half - begin)
-                outs = {}
+        # the k-qubit exchange of ShardedRunner.swap_many, all ranks in lock step
+        pairs = sorted(((gpos - plan.n_local, lpos) for gpos, lpos in seg.pairs), key=lambda t: t[1])
+        gbits, lposs = [t[0] for t in pairs], [t[1] for t in pairs]
+        k = len(pairs)
+        block = 2 ** (plan.n_local - k)
+        for d in range(1, 2**k):
+            def partner_of(r):
+                p = r
+                for j in range(k):
+                    if (d >> j) & 1:
+                        p ^= 1 << gbits[j]
+                return p
+
+            def value_of(p):
+                return sum(((p >> gbits[j]) & 1) << j for j in range(k))
+
+            for begin in range(0, block, chunk):
+                count = min(chunk, block - begin)
+                outs = {r: e.pack(lposs, value_of(partner_of(r)), begin, count) for r, e in enumerate(engines)}
                 for r, e in enumerate(engines):
-                    send_bit = 1 - ((r >> gbit) & 1)
-                    outs[r] = e.pack(lpos, send_bit, begin, count)
-                for r, e in enumerate(engines):
-                    send_bit = 1 - ((r >> gbit) & 1)
-                    e.unpack(outs[r ^ (1 << gbit)], lpos, send_bit, begin, count)
+                    e.unpack(outs[partner_of(r)], lposs, value_of(partner_of(r)), begin, count)
     return engines
 
 
@@ -174,11 +189,13 @@ def _gloo_worker(rank, world, port, n, seed, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("seed", [-1, 11])
-def test_two_process_gloo_exchange(tmp_path, seed):
+@pytest.mark.parametrize("seed,world", [(-1, 2), (11, 2), (-1, 4), (12, 4)])
+def test_multi_process_gloo_exchange(tmp_path, seed, world):
+    """Real torch.distributed (gloo) runs of ShardedRunner: world 2 = single-qubit exchanges, world 4
+    = two-qubit all-to-all exchanges (three pairwise rounds per exchange)."""
     import torch.multiprocessing as mp
 
-    n, world = 11, 2
+    n = 11
     port = 29500 + (os.getpid() + (seed & 0xFF)) % 2000
     mp.spawn(_gloo_worker, args=(world, port, n, seed, str(tmp_path)), nprocs=world, join=True)
     qc = hhl_shaped_circuit(n) if seed < 0 else random_circuit(n, 50, np.random.default_rng(seed), max_k=2)
