@@ -179,6 +179,7 @@ def run_gpu(args):
     # Libraries (NCCL's version banner) write to the C-level stdout: keep fd 1 for the ONE JSON line
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import torch
 
