@@ -208,32 +208,35 @@ class ShardedRunner:
         lposs = [pairs[j][1] for j in order]
         k = len(pairs)
         block = 2 ** (self.plan.n_local - k)
-        chunks = [(b, min(self.chunk, block - b)) for b in range(0, block, self.chunk)]
+        # one flat job list over (round, chunk): the pack / wire / unpack pipeline is not drained between rounds
+        jobs = []
         for d in range(1, 2**k):
             partner = self.rank
             for j in range(k):
                 if (d >> j) & 1:
                     partner ^= 1 << gbits[j]
             value = sum(((partner >> gbits[j]) & 1) << j for j in range(k))  # partner's global bits, as local-bit values
+            for b in range(0, block, self.chunk):
+                jobs.append((partner, value, b, min(self.chunk, block - b)))
 
-            def start(i: int):
-                begin, count = chunks[i]
-                out = self.engine.pack(lposs, value, begin, count, slot=i & 1)
-                inc = self.engine.recv_buffer(count, slot=i & 1)
-                ops = [dist.P2POp(dist.isend, out, partner), dist.P2POp(dist.irecv, inc, partner)]
-                if self.rank > partner:
-                    ops.reverse()
-                self.bytes_sent += out.numel() * out.element_size()
-                return dist.batch_isend_irecv(ops), inc
+        def start(i: int):
+            partner, value, begin, count = jobs[i]
+            out = self.engine.pack(lposs, value, begin, count, slot=i & 1)
+            inc = self.engine.recv_buffer(count, slot=i & 1)
+            ops = [dist.P2POp(dist.isend, out, partner), dist.P2POp(dist.irecv, inc, partner)]
+            if self.rank > partner:
+                ops.reverse()
+            self.bytes_sent += out.numel() * out.element_size()
+            return dist.batch_isend_irecv(ops), inc
 
-            inflight = start(0)
-            for i, (begin, count) in enumerate(chunks):
-                nxt = start(i + 1) if i + 1 < len(chunks) else None
-                reqs, inc = inflight
-                for req in reqs:
-                    req.wait()
-                self.engine.unpack(inc, lposs, value, begin, count)
-                inflight = nxt
+        inflight = start(0)
+        for i, (partner, value, begin, count) in enumerate(jobs):
+            nxt = start(i + 1) if i + 1 < len(jobs) else None
+            reqs, inc = inflight
+            for req in reqs:
+                req.wait()
+            self.engine.unpack(inc, lposs, value, begin, count)
+            inflight = nxt
 
 
 class CudaShardEngine:
