@@ -6,7 +6,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .utils import expand_b_vector, make_matrix_hermitian
+from .utils import (expand_b_vector, extract_x_from_expanded, generate_random_vector, generate_s_sparse_matrix,
+                    is_matrix_well_conditioned, make_matrix_hermitian, vector_uniformity_entropy)
 
 
 class ToyModel:
@@ -75,6 +76,57 @@ class ClassiqDemoExample(ToyModel):
         b = np.array([1, 2, 4, 3])
         b = b / np.linalg.norm(b)
         super().__init__("ClassiqDemoExample", a, b, self.classically_solve(a, b))
+
+
+class RandomNQubitProblem(ToyModel):
+    """Random symmetric ``2**num_qubits`` system: ``A = R + R^T`` with ``R``, ``b`` ~ U(0, 1) from NumPy's
+    global generator (``toymodels.py:188-208``)."""
+
+    def __init__(self, num_qubits: int) -> None:
+        dim = 2**num_qubits
+        r = np.random.rand(dim, dim)
+        a = r + r.T
+        b = np.random.rand(dim)
+        super().__init__(f"RandomNQubitProblem(N={num_qubits})", a, b, self.classically_solve(a, b))
+
+
+def integro_differential_a_matrix(a_matrix: np.ndarray, time_discretization_steps: int) -> np.ndarray:
+    """Block matrix of the explicit-Euler integro-differential toy model (``toymodels.py:211-247``):
+    identity on the block diagonal, ``-(1 + dt*A)`` on the block sub-diagonal, ``dt = 1/steps``."""
+    steps = int(time_discretization_steps)
+    m = a_matrix.shape[0]
+    out = np.zeros((steps * m, steps * m), dtype=np.result_type(a_matrix, float))
+    sub = -np.identity(m) - a_matrix / steps
+    for i in range(steps):
+        out[i * m:(i + 1) * m, i * m:(i + 1) * m] = np.identity(m)
+        if i:
+            out[i * m:(i + 1) * m, (i - 1) * m:i * m] = sub
+    return out
+
+
+class ScalingTestModel(ToyModel):
+    """Scaling study input (``toymodels.py:250-330``): an ``s``-sparse random matrix made Hermitian by
+    embedding, drawn again until its condition number is (``matrix_well_conditioned``) at most
+    ``10 * matrix_size`` / (otherwise) above 1000, and a random ``b`` of the given uniformity."""
+
+    def __init__(self, matrix_size: int = 4, matrix_s: int = 2, matrix_well_conditioned: bool = True,
+                 vector_uniformity: float = 1.0, max_num_iterations: int = 100):
+        b = generate_random_vector(size=matrix_size, uniformity_level=vector_uniformity)
+        entropy = vector_uniformity_entropy(b)
+        b = expand_b_vector(b)
+        assert np.isclose(entropy, vector_uniformity_entropy(b))
+        threshold = 10 * matrix_size if matrix_well_conditioned else 1000
+        a = make_matrix_hermitian(generate_s_sparse_matrix(matrix_size=matrix_size, s_non_zero_entries=matrix_s))
+        tries = 1
+        while matrix_well_conditioned != is_matrix_well_conditioned(a, threshold):
+            a = make_matrix_hermitian(generate_s_sparse_matrix(matrix_size=matrix_size, s_non_zero_entries=matrix_s))
+            tries += 1
+            if tries == max_num_iterations:
+                raise ValueError(f"Could not generate matrix where matrix_well_conditioned={matrix_well_conditioned} "
+                                 f"within {tries} iterations.")
+        csol = extract_x_from_expanded(self.classically_solve(a, b))
+        name = f"TestNxN_n={matrix_size}_s={matrix_s}_c={np.linalg.cond(a):.1f}_e={vector_uniformity_entropy(b):.1f}"
+        super().__init__(name=name, matrix=a, vector=b, csol=csol)
 
 
 class TridiagonalToeplitz(ToyModel):

@@ -81,3 +81,50 @@ def relative_distance_quantum_classical_solution(quantum_solution: np.ndarray, c
             f"different from classical {classical_solution.shape}."
         )
     return float(np.linalg.norm(classical_solution - quantum_solution) / np.linalg.norm(classical_solution) * 100)
+
+
+# ---- input generators of the scaling studies (reference ``utils.py:122-262``; same names and
+# semantics, NumPy's global generator as in the reference so that ``np.random.seed`` pins them) ----
+
+
+def generate_random_vector(size: int, uniformity_level: float) -> np.ndarray:
+    """Normalised random column vector ``(size, 1)``: a fraction ``uniformity_level`` of its entries is
+    drawn from U(0, 1), the rest from N(0, 1), shuffled (0: all normal, 1: all uniform)."""
+    if not 0 <= uniformity_level <= 1:
+        raise ValueError("uniformity_level should be between 0 and 1")
+    if uniformity_level == 0:
+        vec = np.random.randn(size, 1)
+    elif uniformity_level == 1:
+        vec = np.random.rand(size, 1)
+    else:
+        n_uniform = int(size * uniformity_level)
+        vec = np.concatenate((np.random.rand(n_uniform, 1), np.random.randn(size - n_uniform, 1)))
+        np.random.shuffle(vec)
+    return vec / np.linalg.norm(vec)
+
+
+def vector_uniformity_entropy(vector: np.ndarray) -> float:
+    """Shannon entropy (bits) of the vector normalised to unit sum; epsilon 1e-10 inside the log."""
+    v = np.array(vector)
+    p = v / np.sum(v)
+    return float(-np.sum(p * np.log2(p + 1e-10)))
+
+
+def generate_s_sparse_matrix(matrix_size: int, s_non_zero_entries: int) -> np.ndarray:
+    """Square matrix with exactly ``s`` U(0, 1) entries per row at random distinct columns."""
+    if s_non_zero_entries <= 0:
+        raise ValueError("s must be a positive integer")
+    if matrix_size <= 0:
+        raise ValueError("matrix_size must be a positive integer")
+    if s_non_zero_entries > matrix_size:
+        raise ValueError("s cannot be greater than matrix_size")
+    out = np.zeros((matrix_size, matrix_size), dtype=float)
+    for row in range(matrix_size):
+        cols = np.random.choice(matrix_size, s_non_zero_entries, replace=False)
+        out[row, cols] = np.random.rand(s_non_zero_entries)
+    return out
+
+
+def is_matrix_well_conditioned(matrix: np.ndarray, threshold: float = 10.0) -> bool:
+    """2-norm condition number at most ``threshold``."""
+    return bool(np.linalg.cond(matrix) <= threshold)
