@@ -631,10 +631,10 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
       }
       // controls on pass-level fixed bits hold for every tile of the pass (or never: the op is dead)
       if ((op.xc_val & p.fix_mask & op.xc_mask) != (p.fix_val & op.xc_mask & p.fix_mask)) {
-        op.xc_mask = ~0ull;  // never fires
-        op.xc_val = 0;
+        op.xc_mask = ~0ull;  // never fires: no variant has all 64 bits set
+        op.xc_val = ~0ull;
         op.kind = QLS_RS_DIAG;
-        code[o] = 0;
+        code[o] = RS_C_DIAG1;
         continue;
       }
       op.xc_mask &= ~p.fix_mask;

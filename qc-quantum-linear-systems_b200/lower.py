@@ -21,6 +21,7 @@ from __future__ import annotations
 import os
 
 import ctypes as C
+import dataclasses
 import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -386,6 +387,7 @@ class LoweringOptions:
     n_local: int = 0  # 0 -> all qubits local (single GPU)
     batch: bool = False  # one whole-state pass for qls_batch_expect_z (parameterised, n <= 12/13)
     register_stages: bool = True  # also emit the register-stage form of passes that can use it
+    zero_start: bool = False  # the program runs on |0...0> (Statevector(circuit)); a leading state preparation implies it
 
     def resolved_tile_bits(self) -> int:
         if self.tile_bits:
@@ -462,13 +464,16 @@ class LoweredProgram:
         n = self.n_local if n_local is None else n_local
         per = {_abi.QLS_RS_G1: (8, 4), _abi.QLS_RS_G2: (16, 8), _abi.QLS_RS_DIAG: (4, 4), _abi.QLS_RS_MUXRY: (4, 4)}
         tot = 0.0
-        for o in range(self.n_rs_ops):
-            op = self.rs_ops[o]
-            if op.kind not in per:
-                continue
-            c = per[op.kind][1 if (op.flags & _abi.QLS_OP_FLAG_REAL) else 0]
-            nc = bin(op.xc_mask).count("1") + bin(op.ctl_tmask).count("1") + bin(op.ctl_rmask).count("1")
-            tot += c * 0.5**nc * 2.0**n
+        for i in range(self.n_passes):
+            p = self.passes[i]
+            for o in range(p.rs_begin, p.rs_begin + p.rs_count):
+                op = self.rs_ops[o]
+                if op.kind not in per:
+                    continue
+                c = per[op.kind][1 if (op.flags & _abi.QLS_OP_FLAG_REAL) else 0]
+                # controls outside the tile and the pass-level fixed bits (shared controls, qubits still |0>) restrict the tiles
+                nc = bin(op.xc_mask | p.fix_mask).count("1") + bin(op.ctl_tmask).count("1") + bin(op.ctl_rmask).count("1")
+                tot += c * 0.5**nc * 2.0**n
         return tot
 
     def amp_updates(self) -> int:
@@ -523,6 +528,8 @@ class _Emitter:
         self.steps: List[Step] = []
         self.cur: List[Block] = []
         self.cur_high: set = set()
+        # qubits known to be |0> (never acted on non-diagonally since the state was prepared); None: unknown
+        self.zero: Optional[set] = None
 
     # -- pool -----------------------------------------------------------------------------
     def _pool_add(self, arr: np.ndarray) -> int:
@@ -558,11 +565,21 @@ class _Emitter:
             self.cur.append(b)
             self.cur_high |= set(b.touched)
             return
+        if self.zero is not None and b.kind != "init" and b.controls:
+            # a control on a qubit that is still |0>: value 1 never fires (the block is the identity),
+            # value 0 always holds (drop the control)
+            if any(v == 1 and q in self.zero for q, v in b.controls.items()):
+                return
+            if any(q in self.zero for q in b.controls):
+                b = dataclasses.replace(b, controls={q: v for q, v in b.controls.items() if q not in self.zero})
         if b.kind in ("init", "gemm"):
             self.flush()
             if b.kind == "init":
                 self.steps.append(Step("init", qubits=b.targets, amps=b.amps))
+                self.zero = set(range(self.n)) - set(b.targets)
             else:
+                if self.zero is not None:
+                    self.zero -= set(b.targets)
                 mask = sum(1 << q for q in b.controls)
                 val = sum(v << q for q, v in b.controls.items())
                 self.steps.append(Step("gemm", nb=len(b.targets), ctrl_mask=mask, ctrl_val=val, matrix=b.matrix))
@@ -575,6 +592,8 @@ class _Emitter:
         floor = 1 if self.opts.dtype == "fp32" else 0
         if self._fit(self.cur_high | need, min(floor, self.T)) is None:
             raise ValueError(f"block touching {sorted(need)} does not fit a tile of {self.T} bits")
+        if self.zero is not None:
+            self.zero -= need  # eagerly (later blocks of the same pass may be controlled by these qubits), after the flush above
         self.cur.append(b)
         self.cur_high |= need
 
@@ -634,6 +653,21 @@ class _Emitter:
                    if b.kind in ("dense", "diag") else {})
             common = ext if common is None else {q: v for q, v in common.items() if ext.get(q) == v}
         common = common or {}
+        # qubits that are still |0> and that no block of the pass acts on: amplitudes with such a bit set are
+        # zero before and after the pass, so the pass only enumerates the tiles where they are 0 (exact; the
+        # bytes of the skipped tiles are not counted either)
+        zero_fix: List[int] = []
+        if self.zero is not None and not self.opts.batch:
+            touched_pass = set().union(*[set(b.touched) for b in blocks]) if blocks else set()
+            zero_fix = sorted(q for q in self.zero if q < self.n_local and q not in local_pos and q not in touched_pass
+                              and q not in common)
+            while zero_fix:
+                free_try = [q for q in range(self.n_local) if q not in local_pos and q not in common and q not in zero_fix]
+                if len(_segments([(j, q) for j, q in enumerate(free_try)])) <= _abi.QLS_MAX_FSEG:
+                    break
+                zero_fix.pop(0)  # too many index segments: give up the lowest one
+            for q in zero_fix:
+                common[q] = 0
         fix_mask = sum(1 << q for q in common)
         fix_val = sum(v << q for q, v in common.items())
 
@@ -1052,6 +1086,8 @@ def lower_blocks(num_qubits: int, blocks: Sequence[Block], opts: LoweringOptions
             blocks[0] = Block("init", b0.targets, amps=b0.amps * ph[0])
         else:
             blocks.insert(0, Block("diag", (), factors=[((), ph)], n_source=0))
+    if opts.zero_start and not opts.batch:
+        em.zero = set(range(num_qubits))
     for b in blocks:
         em.add(b)
     em.flush()

@@ -8,6 +8,7 @@ amplitudes back as a host ``complex128`` array (only sensible up to ~30 qubits -
 """
 from __future__ import annotations
 
+import dataclasses
 from typing import Any, Optional
 
 import numpy as np
@@ -31,8 +32,9 @@ class Statevector:
             if cached is not None and cached.precision == precision and options is None and fused:
                 self._state, self.num_qubits, self.program = cached._state, cached.num_qubits, cached.program
                 return
-            opts = options or LoweringOptions(dtype=precision)
+            opts = dataclasses.replace(options) if options is not None else LoweringOptions(dtype=precision)
             opts.dtype = precision
+            opts.zero_start = True  # the program below runs on |0...0>: qubits are known to be |0> until first acted on
             lowered = lower_circuit(data, opts, fused=fused)
             self.num_qubits = data.num_qubits
             self.program = DeviceProgram(lowered, device)

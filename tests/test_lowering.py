@@ -1,6 +1,8 @@
 """Lowering pass vs the oracle, through the NumPy interpreter of the binary program format
 (``tests/_emulator.py``): fusion, pass grouping, control handling and table fields are all
 validated on the CPU; the GPU tests then only have to prove the kernels match the same format."""
+import dataclasses
+
 import numpy as np
 import pytest
 
@@ -12,7 +14,7 @@ from qls_b200.lower import LoweringOptions, lower_circuit
 from qls_b200.toymodels import ClassiqDemoExample, Qiskit4QubitExample, VolterraProblem
 
 from _emulator import run_program
-from _util import circuit_to_stream, random_circuit
+from _util import circuit_to_stream, random_circuit, random_unitary
 
 
 def _check(qc, opts, fused=True, tol=1e-12):
@@ -32,6 +34,45 @@ def test_random_circuits(seed, fused):
     opts = LoweringOptions(tile_bits=int(rng.integers(3, 8)), max_high=int(rng.integers(1, 4)),
                            max_fuse_qubits=int(rng.integers(1, 5)))
     _check(qc, opts, fused)
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("form", ["sweep", "rs"])
+def test_zero_qubit_tracking(seed, form):
+    """zero_start: passes only enumerate the tiles in which the qubits that are still |0> are 0, and
+    controls on such qubits are resolved at lowering time.  Sparse circuits (few qubits touched early)
+    so that the fixed bits really occur; both pass forms."""
+    rng = np.random.default_rng(400 + seed)
+    n = 16 if form == "rs" else int(rng.integers(6, 12))
+    qc = QuantumCircuit(n)
+    order = [int(q) for q in rng.permutation(n)]
+    for step, q in enumerate(order):  # wake the qubits up one by one, with controlled ops on sleeping and awake ones in between
+        qc.h(q) if rng.integers(2) else qc.ry(float(rng.uniform(-3, 3)), q)
+        for _ in range(3):
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            kind = rng.integers(4)
+            if kind == 0:
+                qc.cx(a, b)
+            elif kind == 1:
+                qc.cp(float(rng.uniform(-3, 3)), a, b)
+            elif kind == 2:
+                qc.unitary(random_unitary(1, rng), [order[int(rng.integers(step + 1))]])
+            else:
+                from qls_b200.circuit import Gate
+
+                qc.append(Gate("unitary", 1, [], random_unitary(1, rng)).control(1, int(rng.integers(2))), [a, b])
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    opts = LoweringOptions(zero_start=True) if form == "rs" else LoweringOptions(tile_bits=int(rng.integers(3, 6)), max_high=2,
+                                                                                 zero_start=True)
+    low = lower_circuit(qc, opts)
+    assert any(p.fixed_bits > 0 for p in low.pass_info)
+    if form == "rs":
+        assert any(p.rs_stages > 0 for p in low.pass_info)
+    got = run_program(low, form=form)
+    assert np.max(np.abs(got - want)) < 1e-12
+    # same amplitudes as without the tracking
+    ref = run_program(lower_circuit(qc, dataclasses.replace(opts, zero_start=False)), form=form)
+    assert np.max(np.abs(got - ref)) < 1e-13
 
 
 def test_fusion_invariance_and_fewer_passes():
