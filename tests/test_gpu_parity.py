@@ -437,6 +437,24 @@ def test_register_stage_small_tiles(cuda_device):
     assert np.max(np.abs(got - want)) <= TOL64
 
 
+@pytest.mark.parametrize("seed,n", [(0, 14), (1, 17), (2, 20), (3, 20)])
+def test_zero_qubit_tracking_on_gpu(cuda_device, seed, n):
+    """Statevector(circuit) starts from |0...0>: passes skip the tiles in which a qubit that has not been
+    acted on yet is 1, and ops controlled by such qubits are resolved at lowering time (dead ops)."""
+    from qls_b200.lower import LoweringOptions, lower_circuit
+    from qls_b200.statevector import Statevector
+
+    from test_lowering import _wake_up_circuit
+
+    qc = _wake_up_circuit(n, np.random.default_rng(8800 + seed))
+    assert any(p.fixed_bits > 0 for p in lower_circuit(qc, LoweringOptions(dtype="fp64", zero_start=True)).pass_info)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = Statevector(qc).data
+    assert np.max(np.abs(got - want)) <= TOL64
+    got32 = Statevector(qc, precision="fp32").data
+    assert np.max(np.abs(got32 - want)) <= TOL32
+
+
 # ---- edge cases ------------------------------------------------------------------------------------
 
 

@@ -36,17 +36,13 @@ def test_random_circuits(seed, fused):
     _check(qc, opts, fused)
 
 
-@pytest.mark.parametrize("seed", range(16))
-@pytest.mark.parametrize("form", ["sweep", "rs"])
-def test_zero_qubit_tracking(seed, form):
-    """zero_start: passes only enumerate the tiles in which the qubits that are still |0> are 0, and
-    controls on such qubits are resolved at lowering time.  Sparse circuits (few qubits touched early)
-    so that the fixed bits really occur; both pass forms."""
-    rng = np.random.default_rng(400 + seed)
-    n = 16 if form == "rs" else int(rng.integers(6, 12))
+def _wake_up_circuit(n, rng):
+    """Qubits leave |0> one by one, with controlled ops on sleeping and awake qubits in between."""
+    from qls_b200.circuit import Gate
+
     qc = QuantumCircuit(n)
     order = [int(q) for q in rng.permutation(n)]
-    for step, q in enumerate(order):  # wake the qubits up one by one, with controlled ops on sleeping and awake ones in between
+    for step, q in enumerate(order):
         qc.h(q) if rng.integers(2) else qc.ry(float(rng.uniform(-3, 3)), q)
         for _ in range(3):
             a, b = (int(x) for x in rng.choice(n, 2, replace=False))
@@ -58,9 +54,19 @@ def test_zero_qubit_tracking(seed, form):
             elif kind == 2:
                 qc.unitary(random_unitary(1, rng), [order[int(rng.integers(step + 1))]])
             else:
-                from qls_b200.circuit import Gate
-
                 qc.append(Gate("unitary", 1, [], random_unitary(1, rng)).control(1, int(rng.integers(2))), [a, b])
+    return qc
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("form", ["sweep", "rs"])
+def test_zero_qubit_tracking(seed, form):
+    """zero_start: passes only enumerate the tiles in which the qubits that are still |0> are 0, and
+    controls on such qubits are resolved at lowering time.  Sparse circuits (few qubits touched early)
+    so that the fixed bits really occur; both pass forms."""
+    rng = np.random.default_rng(400 + seed)
+    n = 16 if form == "rs" else int(rng.integers(6, 12))
+    qc = _wake_up_circuit(n, rng)
     want = numpy_sv.run(n, circuit_to_stream(qc))
     opts = LoweringOptions(zero_start=True) if form == "rs" else LoweringOptions(tile_bits=int(rng.integers(3, 6)), max_high=2,
                                                                                  zero_start=True)
