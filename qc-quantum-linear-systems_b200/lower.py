@@ -381,7 +381,8 @@ def _mux_expand(angles: np.ndarray, sel: Sequence[int], union: Sequence[int]) ->
 class LoweringOptions:
     dtype: str = "fp64"  # "fp64" (complex128) | "fp32" (complex64)
     tile_bits: int = 0  # 0 -> 12 (fp64) / 13 (fp32)
-    max_high: int = 5  # tile qubits above the contiguous low run
+    max_high: int = 8  # tile qubits above the contiguous low run (runs of >= 2^4 amplitudes = 256 B; 5 -> 2 KB runs: fewer ops per
+    # pass and a higher HBM fraction per pass, but 8 more passes and 12 % more time per 33-qubit solve: profiles/README.md)
     max_fuse_qubits: int = 2  # 2 keeps every block expressible as register-stage micro-ops
     max_diag_qubits: int = 10
     n_local: int = 0  # 0 -> all qubits local (single GPU)
@@ -509,7 +510,7 @@ class _Emitter:
         self.opts = opts
         self.n_local = opts.n_local or n
         self.T = self.n_local if opts.batch else min(opts.resolved_tile_bits(), self.n_local)
-        self.Hmax = 0 if opts.batch else min(opts.max_high, self.T)
+        self.Hmax = 0 if opts.batch else min(int(os.environ.get("QLS_MAX_HIGH", opts.max_high)), self.T)
         self.Lmin = self.T - self.Hmax
         if opts.dtype == "fp32" and self.Lmin < 1:
             self.Lmin = min(1, self.T)
