@@ -85,13 +85,17 @@ __device__ __forceinline__ uint32_t insert_zero_bit(uint32_t x, uint32_t pos) {
   return ((x >> pos) << (pos + 1)) | low;
 }
 
+// (not unrolled: n is 1-3 in practice and a fully unrolled, predicated loop over the 6/16 possible
+// segments costs ~150 issue slots per call -- more than the table lookups it serves)
 __device__ __forceinline__ uint64_t gather_segs64(uint64_t x, const QlsSeg* s, int n) {
   uint64_t r = 0;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) r |= ((x >> s[i].src) & ((1ull << s[i].width) - 1ull)) << s[i].dst;
   return r;
 }
 __device__ __forceinline__ uint32_t gather_segs32(uint32_t x, const QlsSeg* s, int n) {
   uint32_t r = 0;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) r |= ((x >> s[i].src) & ((1u << s[i].width) - 1u)) << s[i].dst;
   return r;
 }
