@@ -241,5 +241,7 @@ class DeviceProgram:
         if tuple(s.qubits) != tuple(range(k)):
             raise NotImplementedError("state preparation must act on the low qubits 0..k-1")
         state.init_basis(None)
-        if state.index_offset == 0:
-            state.write(0, s.amps)
+        rank = state.index_offset >> state.n_local
+        factor = (1.0 if rank == 0 else 0.0) if s.rank_factors is None else s.rank_factors[rank]
+        if factor != 0:
+            state.write(0, s.amps if factor == 1.0 else np.asarray(s.amps) * factor)

@@ -389,6 +389,7 @@ class LoweringOptions:
     batch: bool = False  # one whole-state pass for qls_batch_expect_z (parameterised, n <= 12/13)
     register_stages: bool = True  # also emit the register-stage form of passes that can use it
     zero_start: bool = False  # the program runs on |0...0> (Statevector(circuit)); a leading state preparation implies it
+    awake_after_init: Tuple[int, ...] = ()  # positions that are NOT |0> after the state preparation (folded first gates)
 
     def resolved_tile_bits(self) -> int:
         if self.tile_bits:
@@ -409,6 +410,9 @@ class Step:
     ctrl_mask: int = 0
     ctrl_val: int = 0
     matrix: Optional[np.ndarray] = None
+    # init on a sharded state: rank r writes amps * rank_factors[r] (None: rank 0 only).  Set by the shard planner when
+    # the first gate on a global qubit that is still |0> is folded into the state preparation.
+    rank_factors: Optional[List[complex]] = None
 
 
 @dataclass
@@ -577,7 +581,7 @@ class _Emitter:
             self.flush()
             if b.kind == "init":
                 self.steps.append(Step("init", qubits=b.targets, amps=b.amps))
-                self.zero = set(range(self.n)) - set(b.targets)
+                self.zero = set(range(self.n)) - set(b.targets) - set(self.opts.awake_after_init)
             else:
                 if self.zero is not None:
                     self.zero -= set(b.targets)

@@ -23,6 +23,7 @@ runner drives CUDA shards (``CudaShardEngine``) and the CPU stand-in used by the
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -72,7 +73,7 @@ def _relabel(b: Block, phys: Sequence[int]) -> Block:
 
 
 def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[LoweringOptions] = None,
-                 protect_low: int = 8) -> ShardedPlan:
+                 protect_low: int = 8, fold_first_gates: bool = True) -> ShardedPlan:
     g = int(round(math.log2(world_size)))
     if 2**g != world_size:
         raise ValueError("world size must be a power of two")
@@ -104,16 +105,44 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
         return inf
 
     phys = list(range(n))  # logical -> physical
-    # initial layout: the g logical qubits touched last start on the global positions, except that
-    # an initial state preparation keeps its register on the low local positions
+    # initial layout.  An initial state preparation keeps its register on the low local positions.  A qubit whose
+    # FIRST use is an uncontrolled 1-qubit gate G can start on a global position for free: G|0> = G00|0> + G10|1> is
+    # folded into the state preparation (rank bit b scales the prepared amplitudes by G[b][0]; no communication), which
+    # keeps qubits that stay |0> for long (the HHL flag) LOCAL, where every rank profits from skipping their |1> half.
+    # Remaining global positions: the qubits touched last.
     pinned = set(blocks[0].targets) if blocks and blocks[0].kind == "init" else set()
-    order = sorted((q for q in range(n) if q not in pinned), key=lambda q: (-next_touch(q, 0), -q))
-    global_logical = sorted(order[:g])
+    foldable: Dict[int, int] = {}
+    if blocks and blocks[0].kind == "init" and fold_first_gates:
+        seen: set = set()
+        for i, b in enumerate(blocks[1:], start=1):
+            if b.kind == "dense" and len(b.targets) == 1 and not b.controls and b.targets[0] not in seen \
+                    and b.targets[0] not in pinned:
+                foldable[b.targets[0]] = i
+            seen |= set(b.support)
+    global_logical = sorted(sorted(foldable, reverse=True)[:g])
+    if len(global_logical) < g:
+        order = sorted((q for q in range(n) if q not in pinned and q not in global_logical), key=lambda q: (-next_touch(q, 0), -q))
+        global_logical = sorted(global_logical + order[: g - len(global_logical)])
+    folded = {q: foldable[q] for q in global_logical if q in foldable}
     rest = [q for q in range(n) if q not in global_logical]
     for pos, q in enumerate(rest):
         phys[q] = pos
     for j, q in enumerate(global_logical):
         phys[q] = n_local + j
+    rank_factors: Optional[List[complex]] = None
+    if folded:
+        rank_factors = []
+        for r in range(world_size):
+            f = 1.0 + 0.0j
+            for q, i in folded.items():
+                f *= complex(blocks[i].matrix[(r >> (phys[q] - n_local)) & 1, 0])
+            rank_factors.append(f)
+        drop = set(folded.values())
+        blocks = [b for i, b in enumerate(blocks) if i not in drop]
+        touch_at = [[] for _ in range(n)]
+        for i, b in enumerate(blocks):
+            for q in b.touched:
+                touch_at[q].append(i)
     initial = list(phys)
 
     segments: List[Segment] = []
@@ -123,8 +152,12 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
     def close_local() -> None:
         nonlocal cur
         if cur:
-            o = LoweringOptions(**{**base.__dict__, "n_local": n_local})
-            segments.append(Segment("local", lowered=lower_blocks(n, cur, o)))
+            awake = tuple(initial[q] for q in folded) if not segments else ()
+            o = LoweringOptions(**{**base.__dict__, "n_local": n_local, "awake_after_init": awake})
+            low = lower_blocks(n, cur, o)
+            if not segments and rank_factors is not None and low.steps and low.steps[0].kind == "init":
+                low.steps[0].rank_factors = rank_factors
+            segments.append(Segment("local", lowered=low))
             cur = []
 
     for i, b in enumerate(blocks):
@@ -307,6 +340,7 @@ class ShardedShapedSolver:
         opts.dtype = precision
         self.n, self.nb = circuit.num_qubits, int(nb)
         self.plan = plan_sharded(circuit, self.world, opts)
+        chunk_amps = 1 << int(os.environ.get("QLS_REMAP_CHUNK_LOG2", int(chunk_amps).bit_length() - 1))
         self.engine = CudaShardEngine(self.plan, self.rank, precision, device, chunk_amps)
         self.runner = ShardedRunner(self.plan, self.engine, self.rank, self.world, chunk_amps, dist)
         self.state = self.engine.state
@@ -327,11 +361,16 @@ class ShardedShapedSolver:
 
     def _prepare(self, b_device=None, b_host=None) -> None:
         self.state.init_basis(None)
-        if self.rank == 0:
+        rf = self.plan.segments[0].lowered.steps[0].rank_factors
+        factor = (1.0 if self.rank == 0 else 0.0) if rf is None else rf[self.rank]
+        if factor != 0:
             if b_device is not None:
                 self.state.tensor[: 2**self.nb].copy_(b_device)
+                if factor != 1.0:
+                    self.state.tensor[: 2**self.nb].mul_(factor)
             else:
-                self.state.write(0, self._init_amps if b_host is None else b_host)
+                amps = np.asarray(self._init_amps if b_host is None else b_host)
+                self.state.write(0, amps if factor == 1.0 else amps * factor)
 
     def _run_segments(self) -> None:
         for seg in self.plan.segments:

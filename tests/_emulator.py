@@ -235,8 +235,9 @@ def run_program(lowered, psi0=None, index_offset=0, params=None, form="sweep"):
     elif steps and steps[0].kind == "init":
         s = steps.pop(0)
         assert tuple(s.qubits) == tuple(range(len(s.qubits)))
-        if index_offset == 0:
-            state[: len(s.amps)] = s.amps
+        rank = index_offset >> n
+        f = (1.0 if rank == 0 else 0.0) if s.rank_factors is None else s.rank_factors[rank]
+        state[: len(s.amps)] = np.asarray(s.amps) * f
     elif index_offset == 0:
         state[0] = 1
     for s in steps:

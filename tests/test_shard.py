@@ -38,8 +38,8 @@ class NumpyShardEngine:
             s = steps.pop(0)
             if initialise:
                 self.state[:] = 0
-                if self.rank == 0:
-                    self.state[: len(s.amps)] = s.amps
+                f = (1.0 if self.rank == 0 else 0.0) if s.rank_factors is None else s.rank_factors[self.rank]
+                self.state[: len(s.amps)] = np.asarray(s.amps) * f
         elif initialise:
             self.state[:] = 0
             if self.rank == 0:
@@ -169,6 +169,28 @@ def test_plan_hhl_shaped_fake_comm(world):
     assert plan.initial_layout[: qc.qregs[0].size] == list(range(qc.qregs[0].size))  # data register stays low
     # controls / diagonals on global qubits must not have triggered remaps on their own
     assert plan.n_swaps <= 4 * int(np.log2(world)) + 2
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_first_gates_on_global_qubits_fold_into_the_state_preparation(world):
+    """H on a clock qubit that starts on a global position is folded into the state preparation (every rank
+    writes b / sqrt(2^g)): the flag stays local, and the result is the same as without the fold."""
+    n = 13
+    qc = hhl_shaped_circuit(n)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    got = {}
+    for fold in (True, False):
+        plan = plan_sharded(qc, world, LoweringOptions(**OPTS), protect_low=2, fold_first_gates=fold)
+        rf = plan.segments[0].lowered.steps[0].rank_factors
+        assert (rf is not None) == fold
+        if fold:
+            g = int(np.log2(world))
+            assert np.allclose(rf, [2 ** (-g / 2)] * world)  # Hadamards: every rank gets the same factor
+            assert plan.initial_layout[n - 1] < plan.n_local  # the flag qubit is local
+        engines = _run_fake(plan, world, chunk=1 << 20)
+        got[fold] = _logical_state(plan, [e.state for e in engines])
+        assert np.max(np.abs(got[fold] - want)) < 1e-12
+    assert np.max(np.abs(got[True] - got[False])) < 1e-13
 
 
 def _gloo_worker(rank, world, port, n, seed, out_dir):
