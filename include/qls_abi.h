@@ -212,6 +212,14 @@ int qls_pack_bits(const void* state, void* buffer, int n_local, int dtype, const
                   uint64_t chunk_begin, uint64_t chunk_count, void* stream);
 int qls_unpack_bits(void* state, const void* buffer, int n_local, int dtype, const int* qubits_host, int k, uint64_t value_bits,
                     uint64_t chunk_begin, uint64_t chunk_count, void* stream);
+/* One pairwise round without staging: swap elements [begin, begin+count) of my sub-block (local bits =
+ * my_value_bits) with the same elements of the partner's sub-block (local bits = peer_value_bits) in
+ * `peer_state`, the partner's state buffer mapped into this process (CUDA IPC; peer access over NVLink).
+ * The two GPUs of a pair must be given disjoint element ranges and a device-side barrier before and after. */
+/* cudaDeviceEnablePeerAccess(peer) in the context of `device` (idempotent). */
+int qls_enable_peer_access(int device, int peer);
+int qls_swap_peer(void* state, void* peer_state, int n_local, int dtype, const int* qubits_host, int k,
+                  uint64_t my_value_bits, uint64_t peer_value_bits, uint64_t begin, uint64_t count, void* stream);
 
 #ifdef __cplusplus
 }

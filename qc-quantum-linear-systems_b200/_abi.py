@@ -118,6 +118,8 @@ SYMBOLS = {
     "qls_unpack_bit": (_i, [_vp, _vp, _i, _i, _i, _i, _u64, _u64, _vp]),
     "qls_pack_bits": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _vp]),
     "qls_unpack_bits": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _vp]),
+    "qls_enable_peer_access": (_i, [_i, _i]),
+    "qls_swap_peer": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _u64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

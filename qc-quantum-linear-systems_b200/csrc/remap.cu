@@ -110,3 +110,71 @@ extern "C" int qls_unpack_bits(void* state, const void* buffer, int n_local, int
                                uint64_t value_bits, uint64_t chunk_begin, uint64_t chunk_count, void* stream) {
   return pack_bits_impl<false>(state, const_cast<void*>(buffer), n_local, dtype, qubits, k, value_bits, chunk_begin, chunk_count, stream);
 }
+
+// ---- peer-memory exchange: no staging buffers, no NCCL --------------------------------------------
+// One pairwise round of a k-qubit exchange as ONE kernel per GPU: element t of my sub-block (local bits =
+// my_value) is swapped with element t of the partner's sub-block (local bits = peer_value) through the
+// partner's state mapped into this process (CUDA IPC, peer access over NVLink).  Each GPU of the pair swaps
+// its own half of the element range ([begin, begin + count)), so every element is touched by exactly one
+// GPU: no write-after-read hazard between the two kernels and NVLink is used in both directions by both.
+template <typename V>
+__global__ void __launch_bounds__(256) qls_swap_peer_kernel(V* __restrict__ mine, V* __restrict__ peer, const QlsBitSet bs,
+                                                             uint64_t my_value, uint64_t peer_value, uint64_t begin,
+                                                             uint64_t count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+    uint64_t i = begin + t;
+#pragma unroll
+    for (int m = 0; m < QLS_MAX_REMAP_BITS; ++m)
+      if (m < bs.k) i = ((i >> bs.pos[m]) << (bs.pos[m] + 1)) | (i & ((1ull << bs.pos[m]) - 1ull));
+    const V a = mine[i | my_value];
+    const V b = peer[i | peer_value];
+    mine[i | my_value] = b;
+    peer[i | peer_value] = a;
+  }
+}
+
+extern "C" int qls_swap_peer(void* state, void* peer_state, int n_local, int dtype, const int* qubits, int k,
+                             uint64_t my_value_bits, uint64_t peer_value_bits, uint64_t begin, uint64_t count, void* stream) {
+  QLS_ARG(state && peer_state && qubits, "null pointer");
+  QLS_ARG(k >= 1 && k <= QLS_MAX_REMAP_BITS && k <= n_local, "bad bit count %d", k);
+  QlsBitSet bs;
+  bs.k = k;
+  bs.value = 0;
+  uint64_t mv = 0, pv = 0;
+  for (int m = 0; m < k; ++m) {
+    QLS_ARG(qubits[m] >= 0 && qubits[m] < n_local && (m == 0 || qubits[m] > qubits[m - 1]), "bit positions must be ascending and local");
+    bs.pos[m] = qubits[m];
+    mv |= ((my_value_bits >> m) & 1ull) << qubits[m];
+    pv |= ((peer_value_bits >> m) & 1ull) << qubits[m];
+  }
+  for (int m = k; m < QLS_MAX_REMAP_BITS; ++m) bs.pos[m] = 0;
+  QLS_ARG(begin + count <= (1ull << (n_local - k)), "range outside the sub-block");
+  if (count == 0) return QLS_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint64_t want = (count + 255) / 256;
+  unsigned grid = (unsigned)(want > 148ull * 16 ? 148 * 16 : want);
+  if (dtype == QLS_C128)
+    qls_swap_peer_kernel<double2><<<grid, 256, 0, s>>>(reinterpret_cast<double2*>(state), reinterpret_cast<double2*>(peer_state), bs, mv,
+                                                       pv, begin, count);
+  else
+    qls_swap_peer_kernel<float2><<<grid, 256, 0, s>>>(reinterpret_cast<float2*>(state), reinterpret_cast<float2*>(peer_state), bs, mv, pv,
+                                                      begin, count);
+  QLS_CUDA(cudaGetLastError());
+  return QLS_OK;
+}
+
+// kernels of `device` may dereference memory of `peer` (mapped through CUDA IPC) once this has succeeded
+extern "C" int qls_enable_peer_access(int device, int peer) {
+  QLS_CUDA(cudaSetDevice(device));
+  int can = 0;
+  QLS_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+  QLS_ARG(can, "device %d cannot access device %d directly", device, peer);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();  // clear the sticky-free error state
+    return QLS_OK;
+  }
+  QLS_CUDA(e);
+  return QLS_OK;
+}

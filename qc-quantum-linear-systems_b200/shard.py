@@ -241,6 +241,23 @@ class ShardedRunner:
         lposs = [pairs[j][1] for j in order]
         k = len(pairs)
         block = 2 ** (self.plan.n_local - k)
+        if getattr(self.engine, "peers", None):
+            # peer-memory path: one swap kernel per round and GPU on disjoint halves of the element range, the
+            # partner's state mapped through CUDA IPC; a device-side barrier (tiny all-reduce) before and after
+            self.engine.device_barrier(dist)
+            my_value = sum(((self.rank >> gbits[j]) & 1) << j for j in range(k))
+            for d in range(1, 2**k):
+                partner = self.rank
+                for j in range(k):
+                    if (d >> j) & 1:
+                        partner ^= 1 << gbits[j]
+                value = sum(((partner >> gbits[j]) & 1) << j for j in range(k))
+                half = block // 2
+                begin, count = (0, half) if self.rank < partner else (half, block - half)
+                self.engine.swap_peer(partner, lposs, value, my_value, begin, count)
+                self.bytes_sent += block * self.engine.state.tensor.element_size()
+            self.engine.device_barrier(dist)
+            return
         # one flat job list over (round, chunk): the pack / wire / unpack pipeline is not drained between rounds
         jobs = []
         for d in range(1, 2**k):
@@ -300,6 +317,35 @@ class CudaShardEngine:
     def _stream(self) -> int:
         return int(self.torch.cuda.current_stream().cuda_stream)
 
+    def map_peers(self, dist: Any) -> None:
+        """Map every other rank's state buffer into this process (CUDA IPC handles exchanged through
+        torch.distributed; peer access over NVLink is enabled when the handle is opened)."""
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        fn, args = reduce_tensor(self.state.tensor)
+        world = dist.get_world_size()
+        gathered: List[Any] = [None] * world
+        dist.all_gather_object(gathered, (fn, args))
+        self.peers = {}
+        with self.torch.cuda.device(self.state.device):
+            for r, (f, a) in enumerate(gathered):
+                if r != self.rank:
+                    self.peers[r] = f(*a)
+                    self._abi.check(self.state.lib.qls_enable_peer_access(self.state.tensor.device.index, self.peers[r].device.index))
+            self._tiny = self.torch.zeros(1, dtype=self.torch.float32, device=self.state.tensor.device)
+
+    def device_barrier(self, dist: Any) -> None:
+        dist.all_reduce(self._tiny)  # stream ordered on every rank: nobody passes before everybody's earlier kernels are done
+
+    def swap_peer(self, partner: int, lposs: Sequence[int], my_value: int, peer_value: int, begin: int, count: int) -> None:
+        import ctypes as C
+
+        st = self.state
+        arr = (C.c_int * len(lposs))(*lposs)
+        with self.torch.cuda.device(st.device):
+            self._abi.check(st.lib.qls_swap_peer(st.ptr, self.peers[partner].data_ptr(), st.n_local, st.abi_dtype, arr, len(lposs),
+                                                 my_value, peer_value, begin, count, self._stream()))
+
     def run_local(self, lowered: LoweredProgram, initialise: bool) -> None:
         self.programs[id(lowered)].run(self.state, initialise=initialise)
 
@@ -343,6 +389,8 @@ class ShardedShapedSolver:
         chunk_amps = 1 << int(os.environ.get("QLS_REMAP_CHUNK_LOG2", int(chunk_amps).bit_length() - 1))
         self.engine = CudaShardEngine(self.plan, self.rank, precision, device, chunk_amps)
         self.runner = ShardedRunner(self.plan, self.engine, self.rank, self.world, chunk_amps, dist)
+        if os.environ.get("QLS_REMAP_P2P", "0") == "1":
+            self.engine.map_peers(dist)  # remaps through peer memory instead of pack + NCCL send/recv + unpack
         self.state = self.engine.state
         first = self.plan.segments[0].lowered
         if not (first.steps and first.steps[0].kind == "init"):

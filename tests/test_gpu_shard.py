@@ -9,9 +9,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, out_dir):
+def _worker(rank, world, port, n, out_dir, p2p):
     import torch
     import torch.distributed as dist
+
+    os.environ["QLS_REMAP_P2P"] = "1" if p2p else "0"  # remaps through peer memory (CUDA IPC) or through NCCL send/recv
 
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, here)
@@ -40,8 +42,9 @@ def _worker(rank, world, port, n, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_hhl_shaped_matches_oracle(cuda_device, tmp_path, world):
+def test_sharded_hhl_shaped_matches_oracle(cuda_device, tmp_path, world, p2p):
     import torch
     import torch.multiprocessing as mp
 
@@ -54,8 +57,8 @@ def test_sharded_hhl_shaped_matches_oracle(cuda_device, tmp_path, world):
     from _util import circuit_to_stream
 
     n = 19
-    port = 29600 + (os.getpid() + world) % 2000
-    mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    port = 29600 + (os.getpid() + world + 7 * p2p) % 2000
+    mp.spawn(_worker, args=(world, port, n, str(tmp_path), p2p), nprocs=world, join=True)
     qc = hhl_shaped_circuit(n)
     nb = qc.qregs[0].size
     want = numpy_sv.run(n, circuit_to_stream(qc))
