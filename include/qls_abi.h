@@ -216,6 +216,9 @@ int qls_unpack_bits(void* state, const void* buffer, int n_local, int dtype, con
  * my_value_bits) with the same elements of the partner's sub-block (local bits = peer_value_bits) in
  * `peer_state`, the partner's state buffer mapped into this process (CUDA IPC; peer access over NVLink).
  * The two GPUs of a pair must be given disjoint element ranges and a device-side barrier before and after. */
+/* Map another process's allocation (64-byte cudaIpcMemHandle_t) for kernels of `device`; *out = its base. */
+int qls_ipc_open(const void* handle64, int device, void** out);
+int qls_ipc_close(void* ptr);
 /* cudaDeviceEnablePeerAccess(peer) in the context of `device` (idempotent). */
 int qls_enable_peer_access(int device, int peer);
 int qls_swap_peer(void* state, void* peer_state, int n_local, int dtype, const int* qubits_host, int k,

@@ -119,6 +119,8 @@ SYMBOLS = {
     "qls_pack_bits": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _vp]),
     "qls_unpack_bits": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _vp]),
     "qls_enable_peer_access": (_i, [_i, _i]),
+    "qls_ipc_open": (_i, [_vp, _i, C.POINTER(C.c_void_p)]),
+    "qls_ipc_close": (_i, [_vp]),
     "qls_swap_peer": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _u64, _vp]),
 }
 

@@ -1,6 +1,8 @@
 // Staging kernels for global-qubit remaps of a sharded statevector: the amplitudes whose local bit
 // `qubit` equals `bit_value` are gathered into / scattered from a contiguous buffer that is then
 // exchanged with the partner rank (NCCL send/recv or a peer-memory copy over NVLink).
+#include <string.h>
+
 #include "qls_common.cuh"
 
 // element j of the slab (j in [0, 2^(n-1))) sits at insert_bit(j, qubit, bit_value) in the state
@@ -176,5 +178,22 @@ extern "C" int qls_enable_peer_access(int device, int peer) {
     return QLS_OK;
   }
   QLS_CUDA(e);
+  return QLS_OK;
+}
+
+// Open a CUDA IPC memory handle (64 bytes, from cudaIpcGetMemHandle in the exporting process) in the
+// context of `device`: the runtime maps the allocation for that device and enables peer access to its
+// owner (cudaIpcMemLazyEnablePeerAccess).  *out is the base of the exporting process's allocation.
+extern "C" int qls_ipc_open(const void* handle64, int device, void** out) {
+  QLS_ARG(handle64 && out, "null pointer");
+  QLS_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  QLS_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return QLS_OK;
+}
+extern "C" int qls_ipc_close(void* ptr) {
+  if (ptr) QLS_CUDA(cudaIpcCloseMemHandle(ptr));
   return QLS_OK;
 }

@@ -29,6 +29,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from ._abi import QlsError
 from .circuit import QuantumCircuit, flatten
 from .lower import Block, LoweredProgram, LoweringOptions, fuse, lower_blocks, normalise
 
@@ -320,19 +321,32 @@ class CudaShardEngine:
     def map_peers(self, dist: Any) -> None:
         """Map every other rank's state buffer into this process (CUDA IPC handles exchanged through
         torch.distributed; peer access over NVLink is enabled when the handle is opened)."""
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes as C
 
-        fn, args = reduce_tensor(self.state.tensor)
+        t = self.state.tensor
+        _dev, handle, _size, storage_off, *_ = t.untyped_storage()._share_cuda_()  # cudaIpcGetMemHandle of the allocation
+        offset = int(storage_off) + t.storage_offset() * t.element_size()
         world = dist.get_world_size()
         gathered: List[Any] = [None] * world
-        dist.all_gather_object(gathered, (fn, args))
+        handle = bytes(handle)
+        if len(handle) == 65:  # newer torch prefixes the 64-byte cudaIpcMemHandle_t with the allocation kind
+            if handle[:1] != b"c":
+                raise QlsError("state buffer is not a plain cudaMalloc allocation (expandable segments?): no IPC handle")
+            handle = handle[1:]
+        if len(handle) != 64:
+            raise QlsError(f"unexpected CUDA IPC handle size {len(handle)}")
+        dist.all_gather_object(gathered, (handle, offset))
         self.peers = {}
+        self._ipc_bases = []
+        for r, (h, off) in enumerate(gathered):
+            if r != self.rank:
+                base = C.c_void_p()
+                buf = C.create_string_buffer(h, 64)
+                self._abi.check(self.state.lib.qls_ipc_open(C.cast(buf, C.c_void_p), t.device.index, C.byref(base)))
+                self._ipc_bases.append(base)
+                self.peers[r] = base.value + off  # device pointer to rank r's state, valid in kernels of this device
         with self.torch.cuda.device(self.state.device):
-            for r, (f, a) in enumerate(gathered):
-                if r != self.rank:
-                    self.peers[r] = f(*a)
-                    self._abi.check(self.state.lib.qls_enable_peer_access(self.state.tensor.device.index, self.peers[r].device.index))
-            self._tiny = self.torch.zeros(1, dtype=self.torch.float32, device=self.state.tensor.device)
+            self._tiny = self.torch.zeros(1, dtype=self.torch.float32, device=t.device)
 
     def device_barrier(self, dist: Any) -> None:
         dist.all_reduce(self._tiny)  # stream ordered on every rank: nobody passes before everybody's earlier kernels are done
@@ -343,7 +357,7 @@ class CudaShardEngine:
         st = self.state
         arr = (C.c_int * len(lposs))(*lposs)
         with self.torch.cuda.device(st.device):
-            self._abi.check(st.lib.qls_swap_peer(st.ptr, self.peers[partner].data_ptr(), st.n_local, st.abi_dtype, arr, len(lposs),
+            self._abi.check(st.lib.qls_swap_peer(st.ptr, self.peers[partner], st.n_local, st.abi_dtype, arr, len(lposs),
                                                  my_value, peer_value, begin, count, self._stream()))
 
     def run_local(self, lowered: LoweredProgram, initialise: bool) -> None:
