@@ -329,10 +329,11 @@ class CudaShardEngine:
         world = dist.get_world_size()
         gathered: List[Any] = [None] * world
         handle = bytes(handle)
-        if len(handle) == 65:  # newer torch prefixes the 64-byte cudaIpcMemHandle_t with the allocation kind
-            if handle[:1] != b"c":
+        # torch prefixes the 64-byte cudaIpcMemHandle_t with [version byte,] allocation kind ('c' = plain cudaMalloc)
+        if len(handle) in (65, 66):
+            if handle[len(handle) - 65:len(handle) - 64] != b"c":
                 raise QlsError("state buffer is not a plain cudaMalloc allocation (expandable segments?): no IPC handle")
-            handle = handle[1:]
+            handle = handle[-64:]
         if len(handle) != 64:
             raise QlsError(f"unexpected CUDA IPC handle size {len(handle)}")
         dist.all_gather_object(gathered, (handle, offset))
