@@ -316,14 +316,20 @@ def run_gpu(args):
         if world > 1:
             sent = st["remap_bytes_sent_per_gpu"]
             ms = getattr(solver, "remap_ms", 0.0)
-            launches_per_step += 2 * max(1, sent // (S * solver.runner.chunk))  # one pack + one unpack per chunk on the wire
+            p2p = bool(getattr(solver.engine, "peers", None))
+            if p2p:  # one swap kernel per pairwise round
+                launches_per_step += sum(2 ** len(sg.pairs) - 1 for sg in solver.plan.segments if sg.kind == "swap")
+            else:  # one pack + one unpack per chunk on the wire
+                launches_per_step += 2 * max(1, sent // (S * solver.runner.chunk))
             remap = {"remapped_qubits_per_step": st["remaps"], "exchanges_per_step": st["remap_exchanges"],
                      "bytes_sent_per_gpu": sent, "ms_per_step": ms,
                      "achieved_gbs_per_direction": (sent / (ms * 1e-3) / 1e9) if ms else None, "peak": 770.0,
                      "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
                      "frac": (sent / (ms * 1e-3) / 1e9 / 770.0) if ms else None,
-                     "includes": "pack + NCCL send/recv + unpack, chunked; a k-qubit exchange is one all-to-all of 2^k - 1 "
-                                 "pairwise rounds; not overlapped with compute"}
+                     "transport": "peer memory (CUDA IPC over NVLink): one swap kernel per pairwise round" if p2p
+                                  else "pack + NCCL send/recv + unpack, chunked",
+                     "includes": "a k-qubit exchange is one all-to-all of 2^k - 1 pairwise rounds, device barriers included; "
+                                 "not overlapped with compute"}
         line = {
             "metric": METRIC, "value": amp_updates / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
