@@ -1,23 +1,28 @@
-// Register-stage tile-pass kernel (the fast path for full-size tiles).
+// Register-stage tile-pass kernel (the fast path for full-size tiles; 98 % of the GPU time of a solve).
 //
-// Persistent CTAs (2 per SM, 256 threads).  A tile of 2^T amplitudes (T = 12 complex128 /
+// Persistent CTAs (2 per SM, 256 threads, 128 registers).  A tile of 2^T amplitudes (T = 12 complex128 /
 // 13 complex64 -> 64 KB) lives in the REGISTERS of the CTA: every thread holds 2^KR amplitudes
 // (KR = 4 / 5: the stage's "register qubits"), the remaining 8 tile bits are the thread index.  All
 // micro-ops of a stage -- 1- and 2-qubit dense blocks on register qubits, diagonal tables,
 // multiplexed RY -- run on registers with compile-time register indices; shared memory is touched
 // only to re-distribute the tile between stages (one XOR-swizzled write + one read) and to make
-// the global accesses coalesced when the stage's lanes are not the low tile bits.
+// the global accesses coalesced when a stage's two lowest tile bits are not lane bits.
 //
-// What keeps the FP64 pipe fed (ncu of the previous version: 27 % FP64-pipe activity, 60 % of the
-// issue slots spent on address/decode work, long-scoreboard stalls on matrix loads):
-//   * the whole pass description -- header, micro-op records AND gate matrices -- sits in
-//     __constant__ memory (uploaded per pass, stream ordered).  Every thread reads it at a
-//     warp-uniform address, so records decode on the uniform datapath and the DFMAs take their
-//     matrix element straight from a uniform register: no per-thread load in the inner loops;
-//   * stages are entered lazily: a stage whose ops are all switched off for this tile by controls
-//     outside the tile costs nothing, and a tile on which no op fires is neither read nor written;
-//   * tile loads/stores are streaming (ld/st.global.cs, cp.async.cg) so that L1 keeps the phase tables;
-//   * diagonal tables / multiplexer angles are fetched in batches before they are used.
+// What keeps the FP64 pipe fed (profiles/README.md has the ncu history: 27 % -> 47 % FP64-pipe activity
+// on the data-register passes, 90 % for the gate core alone):
+//   * the whole pass description -- header, micro-op records, gate matrices and one straight-line
+//     STEP LIST per assignment of the control qubits outside the tile -- sits in __constant__ memory
+//     (built by qls_rs_build_images, uploaded per pass, stream ordered).  Every thread reads it at a
+//     warp-uniform address, so steps decode on the uniform datapath and the DFMAs take their matrix
+//     element straight from a uniform register: no per-thread load in the gate loops, no control test,
+//     no stage bookkeeping in the kernel;
+//   * a step list enters a stage only if one of its ops fires for that control assignment, and a tile on
+//     which no op fires is neither read nor written;
+//   * tile loads/stores bypass L1 (ld/st.global.cg, cp.async.cg) so that L1 keeps the phase tables;
+//     tables whose index does not depend on the lane are fetched once per warp (shared-memory scratch line).
+// Variants that were measured and dropped (two token-passing warp-groups per CTA, 2^11-amplitude tiles with
+// four CTAs per SM, 32 amplitudes per thread, L2 prefetch of the next tile) are described in profiles/README.md;
+// the first two are still selectable (QLS_RS_PINGPONG=1, LoweringOptions.tile_bits=11).
 #include <stdlib.h>
 #include <string.h>
 
