@@ -169,6 +169,9 @@ class DeviceProgram:
                 first = 1
             elif initialise:
                 state.init_basis(0 if state.index_offset == 0 else None)
+            elif lw.zero_start:
+                raise _abi.QlsError("this program was lowered for a |0...0> input (zero-qubit tracking): run it with initialise=True "
+                               "or lower the circuit without LoweringOptions.zero_start")
             for i in range(first, len(steps)):
                 s = steps[i]
                 if s.kind == "passes":

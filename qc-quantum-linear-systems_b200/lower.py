@@ -444,6 +444,7 @@ class LoweredProgram:
     pass_info: List[PassInfo]
     n_source_gates: int
     global_phase: float
+    zero_start: bool = False  # lowered for |0...0> input: passes skip tiles that a still-|0> qubit makes zero
 
     @property
     def n_passes(self) -> int:
@@ -1101,7 +1102,7 @@ def lower_blocks(num_qubits: int, blocks: Sequence[Block], opts: LoweringOptions
     rs_ops = (_abi.QlsRsOp * max(1, len(em.rs_ops)))(*em.rs_ops)
     pool = np.frombuffer(bytes(em.pool) if em.pool else b"\0" * 16, dtype=np.uint8).copy()
     return LoweredProgram(num_qubits, em.n_local, opts.dtype, em.steps, passes, ops, rs_ops, len(em.rs_ops), pool,
-                          em.pass_info, n_source_gates, global_phase)
+                          em.pass_info, n_source_gates, global_phase, bool(opts.zero_start and not opts.batch))
 
 
 def lower_leaves(num_qubits: int, leaves: Sequence[Leaf], global_phase: float = 0.0,
