@@ -154,7 +154,8 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
         nonlocal cur
         if cur:
             awake = tuple(initial[q] for q in folded) if not segments else ()
-            o = LoweringOptions(**{**base.__dict__, "n_local": n_local, "awake_after_init": awake})
+            o = LoweringOptions(**{**base.__dict__, "n_local": n_local, "awake_after_init": awake,
+                                   "zero_start": False})  # a leading state preparation implies the tracking; never after a remap
             low = lower_blocks(n, cur, o)
             if not segments and rank_factors is not None and low.steps and low.steps[0].kind == "init":
                 low.steps[0].rank_factors = rank_factors
