@@ -45,7 +45,7 @@ struct RsHeader {  // 256 bytes
   int32_t n_cbits;     // control qubits outside the tile whose values select the step list (variant)
   int32_t n_stages;
   uint32_t steps_off;  // byte offset of RsStep[] in the image body
-  uint32_t pad0;
+  uint32_t rtw_off;    // byte offset of uint32_t[n_recs][32]: rt[] widened to 32-bit words (single precision only)
   uint8_t cbit[8];     // their global index bit positions
   uint8_t high[QLS_MAX_HIGH];
   QlsSeg fseg[QLS_MAX_FSEG];
@@ -188,6 +188,15 @@ __device__ __forceinline__ uint32_t rs_tidx(uint32_t base, const uint32_t (&d)[K
   return t;
 }
 
+// The same contribution read from the image's widened copy of rt[] (32-bit words, RsHeader.rtw_off).  The
+// single-precision kernel must use this form: with rs_tidx over five 16-bit rt[] loads ptxas leaves the uniform
+// datapath for the WHOLE step loop (FFMA..UR count 0, gate matrices fetched per thread with LDC).
+template <typename V, int KR>
+__device__ __forceinline__ uint32_t rs_tcombo(const uint32_t (&d)[KR], const uint32_t* __restrict__ rw, int r) {
+  if constexpr (sizeof(V) == 8) return rw[r];
+  else return rs_tidx<KR>(0u, d, r);
+}
+
 // one phase per thread: the table looks at no register qubit and there is no register-bit control
 template <typename V, int A>
 __device__ __forceinline__ void rs_diag1(V (&a)[A], const V* __restrict__ table, uint32_t ti0, bool tok) {
@@ -201,10 +210,11 @@ __device__ __forceinline__ void rs_diag1(V (&a)[A], const V* __restrict__ table,
 }
 
 template <typename V, int A, int KR, bool CTL>
-__device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
+__device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const uint32_t* __restrict__ rw, const V* __restrict__ table,
+                                        uint32_t ti0, bool tok) {
   uint32_t d[KR];
 #pragma unroll
-  for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
+  for (int j = 0; j < KR; ++j) d[j] = sizeof(V) == 8 ? 0u : (uint32_t)op.rt[1 << j];
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
   constexpr int CH = 4;  // phases fetched per batch (register budget)
   const V* tb = table + ti0;  // the register-qubit fields are disjoint from ti0: | is +, and they are warp-uniform
@@ -212,7 +222,7 @@ __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* _
   for (int c = 0; c < A; c += CH) {
     V ph[CH];
 #pragma unroll
-    for (int r = 0; r < CH; ++r) ph[r] = __ldg(tb + rs_tidx<KR>(0u, d, c + r));  // index is valid whatever the controls say
+    for (int r = 0; r < CH; ++r) ph[r] = __ldg(tb + rs_tcombo<V, KR>(d, rw, c + r));  // index is valid whatever the controls say
 #pragma unroll
     for (int r = 0; r < CH; ++r)
       if (!CTL || (tok && (((uint32_t)(c + r) & rm) == rv))) a[c + r] = cmul(a[c + r], ph[r]);
@@ -226,13 +236,17 @@ __device__ __forceinline__ void rs_diag(V (&a)[A], const QlsRsOp& op, const V* _
 // CTL: control on register qubits only (warp-uniform predicate; a per-thread predicate between the two
 // warp barriers makes ptxas give up the uniform datapath for the whole step loop).
 template <typename V, int A, int KR, bool CTL>
-__device__ __forceinline__ void rs_diagw(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0,
-                                         V* __restrict__ scr, int lane) {
+__device__ __forceinline__ void rs_diagw(V (&a)[A], const QlsRsOp& op, const uint32_t* __restrict__ rw, const V* __restrict__ table,
+                                         uint32_t ti0, V* __restrict__ scr, int lane) {
   {  // every lane takes part (lanes >= A duplicate entry lane % A): no divergent branch in the step loop
     const int e = lane & (A - 1);
     uint32_t t = ti0;
+    if constexpr (sizeof(V) == 8) {
+      t |= rw[e];
+    } else {
 #pragma unroll
-    for (int j = 0; j < KR; ++j) t |= ((e >> j) & 1) ? (uint32_t)op.rt[1 << j] : 0u;
+      for (int j = 0; j < KR; ++j) t |= ((e >> j) & 1) ? (uint32_t)op.rt[1 << j] : 0u;
+    }
     scr[e] = __ldg(&table[t]);
   }
   __syncwarp();
@@ -246,10 +260,11 @@ __device__ __forceinline__ void rs_diagw(V (&a)[A], const QlsRsOp& op, const V* 
 }
 
 template <typename V, int A, int KR, int RQ>
-__device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* __restrict__ table, uint32_t ti0, bool tok) {
+__device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const uint32_t* __restrict__ rw, const V* __restrict__ table,
+                                         uint32_t ti0, bool tok) {
   uint32_t d[KR];
 #pragma unroll
-  for (int j = 0; j < KR; ++j) d[j] = op.rt[1 << j];
+  for (int j = 0; j < KR; ++j) d[j] = sizeof(V) == 8 ? 0u : (uint32_t)op.rt[1 << j];
   const uint32_t rm = op.ctl_rmask, rv = op.ctl_rval;
   constexpr int CH = 4;
   const V* tb = table + ti0;
@@ -260,7 +275,7 @@ __device__ __forceinline__ void rs_muxry(V (&a)[A], const QlsRsOp& op, const V* 
     for (int q = 0; q < CH; ++q) {
       const int p = c + q;
       const int i0 = ((p >> RQ) << (RQ + 1)) | (p & ((1 << RQ) - 1));
-      cs[q] = __ldg(tb + rs_tidx<KR>(0u, d, i0));
+      cs[q] = __ldg(tb + rs_tcombo<V, KR>(d, rw, i0));
     }
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
@@ -379,6 +394,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
       ++s;
       const QlsRsOp& op = recs[st.rec];
       const V* M = reinterpret_cast<const V*>(c_img.body + 16u * st.moff);
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(c_img.body + c_img.h.rtw_off) + 32u * st.rec;  // single precision only
 #ifdef QLS_RS_TIMING  // timing experiments only (profiles/README.md): switch parts of the kernel off
       const bool skip = KR == 4 && sizeof(V) == 16 && dbg != 0 && (((dbg & 1u) && st.code >= RS_C_G1) || ((dbg & 2u) && st.code == RS_C_TRANS) ||
                                     ((dbg & 4u) && st.code >= RS_C_DIAG && st.code < RS_C_G1));
@@ -476,7 +492,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
         case RS_C_DIAGWC: {
           const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
           const V* table = reinterpret_cast<const V*>(pool + op.pool_off);
-          rs_diagw<V, A, KR, true>(a, op, table, ti0, wscr, tid & 31);  // one instantiation: (r & 0) == 0 without a control
+          rs_diagw<V, A, KR, true>(a, op, rw, table, ti0, wscr, tid & 31);  // one instantiation: (r & 0) == 0 without a control
           break;
         }
         case RS_C_DIAG:
@@ -484,8 +500,8 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
         case RS_C_DIAG1: {
           const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
           const V* table = reinterpret_cast<const V*>(pool + op.pool_off);
-          if (st.code == RS_C_DIAG) rs_diag<V, A, KR, false>(a, op, table, ti0, true);
-          else if (st.code == RS_C_DIAGC) rs_diag<V, A, KR, true>(a, op, table, ti0, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval);
+          if (st.code == RS_C_DIAG) rs_diag<V, A, KR, false>(a, op, rw, table, ti0, true);
+          else if (st.code == RS_C_DIAGC) rs_diag<V, A, KR, true>(a, op, rw, table, ti0, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval);
           else rs_diag1<V, A>(a, table, ti0, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval);
           break;
         }
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
   case RS_C_MUX + q: {                                                                                               \
     const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;                                                  \
     const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg); \
-    rs_muxry<V, A, KR, q>(a, op, reinterpret_cast<const V*>(pool + op.pool_off), ti0, tok);                          \
+    rs_muxry<V, A, KR, q>(a, op, rw, reinterpret_cast<const V*>(pool + op.pool_off), ti0, tok);                          \
     break;                                                                                                           \
   }
         QLS_MUX_CASE(0)
@@ -740,13 +756,25 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
       h.vstart[v] = (uint16_t)first;
     }
     h.steps_off = (uint32_t)(recs_bytes + mats.size());
-    const size_t total = sizeof(RsHeader) + recs_bytes + mats.size() + steps.size() * sizeof(RsStep);
+    // complex64 kernel: table-index contribution of every register combination as 32-bit words (see rs_tcombo)
+    std::vector<uint32_t> rtw;
+    if (KR == 5) {
+      rtw.assign(recs.size() * 32, 0u);
+      for (size_t o = 0; o < recs.size(); ++o)
+        if (recs[o].kind == QLS_RS_DIAG || recs[o].kind == QLS_RS_MUXRY)
+          for (int r = 0; r < 32; ++r)
+            for (int j = 0; j < KR; ++j)
+              if ((r >> j) & 1) rtw[o * 32 + r] |= recs[o].rt[1 << j];
+      h.rtw_off = (uint32_t)(h.steps_off + steps.size() * sizeof(RsStep));
+    }
+    const size_t total = sizeof(RsHeader) + recs_bytes + mats.size() + steps.size() * sizeof(RsStep) + rtw.size() * sizeof(uint32_t);
     if (total > (size_t)RS_IMG_BYTES || steps.size() >= RS_IDLE || (mats_off + mats.size()) / 16 > 0xFFFFu) continue;
     std::vector<unsigned char> img(total, 0);
     memcpy(img.data(), &h, sizeof(h));
     memcpy(img.data() + sizeof(RsHeader), recs.data(), recs_bytes);
     memcpy(img.data() + sizeof(RsHeader) + recs_bytes, mats.data(), mats.size());
     memcpy(img.data() + sizeof(RsHeader) + h.steps_off, steps.data(), steps.size() * sizeof(RsStep));
+    if (!rtw.empty()) memcpy(img.data() + sizeof(RsHeader) + h.rtw_off, rtw.data(), rtw.size() * sizeof(uint32_t));
     while (img.size() % 16) img.push_back(0);
     prog->rs_img_bytes[i] = (uint32_t)img.size();
     prog->rs_img_kr[i] = (uint8_t)KR;
