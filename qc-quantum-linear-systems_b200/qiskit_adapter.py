@@ -1,5 +1,5 @@
 """Adapter for real qiskit circuits (used only when qiskit is importable; it is not in the build
-image, so this module is import-guarded and exercised by no test here).
+image, so this module never imports it and is tested with duck-typed stand-ins, tests/test_qiskit_adapter.py).
 
 ``from_qiskit`` walks ``QuantumCircuit.data`` the way ``Statevector._evolve_instruction`` does
 (reference call sites ``hhl_qiskit_implementation.py:49``, ``vqls_qiskit_implementation.py:65``):
