@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           }
           break;
         }
+#ifndef QLS_RS_NO_LOADS
         case RS_C_LOAD_S: {
           uint32_t cq[KR], lq[KR];
           rs_stage_bits<KR, SH>(op, cq, lq);
@@ -431,6 +432,8 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
           break;
         }
+#endif
+#ifndef QLS_RS_NO_TRANS
         case RS_C_TRANS: {
           const QlsRsOp& from = recs[st.aux];
           uint32_t cq[KR], lq[KR];
@@ -447,6 +450,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           for (int r = 0; r < A; ++r) a[r] = sm[rs_addr<KR>(mytb, cq, r)];
           break;
         }
+#endif
         case RS_C_STORE_D: {
           if (GROUPS > 1 && st.moff == RS_F_RELEASE) {
             RS_SYNC();
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           }
           break;
         }
+#ifndef QLS_RS_NO_STORES
         case RS_C_STORE_S: {
           uint32_t cq[KR], lq[KR];
           rs_stage_bits<KR, SH>(op, cq, lq);
@@ -479,6 +484,8 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           }
           break;
         }
+#endif
+#ifndef QLS_RS_NO_ACQ
         case RS_C_ACQ: {
           if (GROUPS > 1) {
             if (tid == 0) {
@@ -488,6 +495,8 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           }
           break;
         }
+#endif
+#ifndef QLS_RS_NO_DIAGW
         case RS_C_DIAGW:
         case RS_C_DIAGWC: {
           const uint32_t ti0 = (uint32_t)gather_segs64(gbase, op.xseg, op.n_xseg) | gather_segs32((uint32_t)tid, op.tseg, op.n_tseg);
@@ -495,6 +504,8 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           rs_diagw<V, A, KR, true>(a, op, rw, table, ti0, wscr, tid & 31);  // one instantiation: (r & 0) == 0 without a control
           break;
         }
+#endif
+#ifndef QLS_RS_NO_DIAG
         case RS_C_DIAG:
         case RS_C_DIAGC:
         case RS_C_DIAG1: {
@@ -505,6 +516,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
           else rs_diag1<V, A>(a, table, ti0, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval);
           break;
         }
+#endif
 #define QLS_MUX_CASE(q)                                                                                              \
   case RS_C_MUX + q: {                                                                                               \
     const bool tok = ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval;                                                  \
@@ -512,10 +524,12 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
     rs_muxry<V, A, KR, q>(a, op, rw, reinterpret_cast<const V*>(pool + op.pool_off), ti0, tok);                          \
     break;                                                                                                           \
   }
+#ifndef QLS_RS_NO_MUX
         QLS_MUX_CASE(0)
         QLS_MUX_CASE(1)
         QLS_MUX_CASE(2)
         QLS_MUX_CASE(3)
+#endif
 #define QLS_G1_CASE(q)                                                                                               \
   case RS_C_G1 + 4 * q + 0: rs_g1<V, A, q, false, false>(a, M, true, 0, 0); break;                                   \
   case RS_C_G1 + 4 * q + 2: rs_g1<V, A, q, true, false>(a, M, true, 0, 0); break;                                    \
@@ -525,10 +539,12 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
   case RS_C_G1 + 4 * q + 3:                                                                                          \
     rs_g1<V, A, q, true, true>(a, M, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval, op.ctl_rmask, op.ctl_rval);       \
     break;
+#ifndef QLS_RS_NO_G1
         QLS_G1_CASE(0)
         QLS_G1_CASE(1)
         QLS_G1_CASE(2)
         QLS_G1_CASE(3)
+#endif
 #define QLS_G2_CASE(p, q)                                                                                            \
   case RS_C_G2 + 4 * rs_pair(p, q) + 0: rs_g2<V, A, p, q, false, false>(a, M, true, 0, 0); break;                    \
   case RS_C_G2 + 4 * rs_pair(p, q) + 2: rs_g2<V, A, p, q, true, false>(a, M, true, 0, 0); break;                     \
@@ -538,13 +554,16 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
   case RS_C_G2 + 4 * rs_pair(p, q) + 3:                                                                              \
     rs_g2<V, A, p, q, true, true>(a, M, ((uint32_t)tid & op.ctl_tmask) == op.ctl_tval, op.ctl_rmask, op.ctl_rval);    \
     break;
+#ifndef QLS_RS_NO_G2
         QLS_G2_CASE(0, 1)
         QLS_G2_CASE(0, 2)
         QLS_G2_CASE(0, 3)
         QLS_G2_CASE(1, 2)
         QLS_G2_CASE(1, 3)
         QLS_G2_CASE(2, 3)
+#endif
         default:
+#ifndef QLS_RS_NO_KR5
           if constexpr (KR >= 5) {
             switch (st.code) {
               QLS_MUX_CASE(4)
@@ -555,6 +574,7 @@ __global__ void __launch_bounds__(GROUPS << (T - KR), CTAS)
               QLS_G2_CASE(3, 4)
             }
           }
+#endif
           break;
 #undef QLS_MUX_CASE
 #undef QLS_G1_CASE
@@ -802,10 +822,18 @@ int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_i
     const char* e = getenv("QLS_RS_PINGPONG");
     pingpong = e ? atoi(e) : 0;
   }
+  // QLS_RS_ONLY_F32 / QLS_RS_ONLY_F64 and the QLS_RS_NO_<step> guards in the kernel exist for tools/uniformity_bisect.py
+  // (compile-only experiments on ptxas' uniform-datapath decision); a product build defines none of them
+#ifndef QLS_RS_ONLY_F32
   if (prog->dtype == QLS_C128) {
     if (p.tile_bits == 11) return launch_rs<double, 11, 4, 4, 1>(prog, p, pass_index, state, n_local, index_offset, stream);
     if (pingpong) return launch_rs<double, 12, 4, 1, 2>(prog, p, pass_index, state, n_local, index_offset, stream);
     return launch_rs<double, 12, 4, 2, 1>(prog, p, pass_index, state, n_local, index_offset, stream);
   }
+#endif
+#ifndef QLS_RS_ONLY_F64
   return launch_rs<float, 13, 5, 2, 1>(prog, p, pass_index, state, n_local, index_offset, stream);
+#else
+  return QLS_ERR_ARG;
+#endif
 }
