@@ -1,86 +1,95 @@
-"""``solve_vqls_qiskit`` on the B200 engine: same signature, return tuple, side effects and error
-behaviour as the reference's
-``quantum_linear_systems/implementations/vqls_qiskit_implementation.py:24-126``.  The default
-``estimator`` is a ``B200Estimator`` (created on first use, then shared across calls like the
-reference's import-time ``Estimator()`` default, ``:28``)."""
+"""``solve_vqls_qiskit`` on the B200 engine.
+
+Interface of the reference's ``quantum_linear_systems/implementations/vqls_qiskit_implementation.py:24-126``:
+``(matrix_a, vector_b, ansatz=None, estimator=..., optimizer_name="cobyla", optimizer_max_iter=250,
+show_circuit=False) -> (x, qasm3 text, depth, width, seconds)``, ``ValueError`` for an unknown optimizer, the
+``vqls_qiskit_circuit.qasm3`` file in the working directory, and ``postprocess_solution``.
+
+``estimator`` is the reference's plug-in hole (it swaps in a Braket estimator at ``aws_execution.py:174-182``);
+the default here is one process-wide ``B200Estimator`` -- created on first use instead of at import time
+(``:28`` of the reference), so importing this module does not need a GPU.  ``seed`` fixes the optimizer's random
+start point, which the reference leaves to ``vqls_prototype``."""
 from __future__ import annotations
 
 import time
-from typing import Any, Optional, Tuple
+from typing import Any, Callable, Dict, Optional, Tuple
 
 import numpy as np
 
+from .. import utils
 from ..circuit import QuantumCircuit
 from ..library import RealAmplitudes
-from ..utils import circuit_to_qasm3, extract_x_from_expanded, is_expanded
 from ..vqls import COBYLA, SLSQP, VQLS
 
-_DEFAULT_ESTIMATOR = None
+QASM_FILE = "vqls_qiskit_circuit.qasm3"
+_OPTIMIZERS: Dict[str, Callable[..., Any]] = {"cobyla": COBYLA, "slsqp": SLSQP}
+_shared_estimator: Any = None
 
 
-def _default_estimator():
-    global _DEFAULT_ESTIMATOR
-    if _DEFAULT_ESTIMATOR is None:
+def _default_estimator() -> Any:
+    global _shared_estimator
+    if _shared_estimator is None:
         from ..estimator import B200Estimator
 
-        _DEFAULT_ESTIMATOR = B200Estimator()
-    return _DEFAULT_ESTIMATOR
+        _shared_estimator = B200Estimator()
+    return _shared_estimator
+
+
+def _make_optimizer(name: str, max_iter: int) -> Any:
+    try:
+        factory = _OPTIMIZERS[name.lower()]
+    except KeyError:
+        raise ValueError(f"Invalid optimizer_name: {name}") from None
+    return factory(maxiter=max_iter, disp=True)
 
 
 def solve_vqls_qiskit(matrix_a: np.ndarray, vector_b: np.ndarray, ansatz: Optional[QuantumCircuit] = None,
                       estimator: Any = None, optimizer_name: str = "cobyla", optimizer_max_iter: int = 250,
                       show_circuit: bool = False, seed: Optional[int] = None) -> Tuple[np.ndarray, str, int, int, float]:
-    start_time = time.time()
-    np.set_printoptions(precision=3, suppress=True)
-
-    if ansatz is None:
-        ansatz = RealAmplitudes(num_qubits=int(np.log2(matrix_a.shape[0])), entanglement="full", reps=3,
-                                insert_barriers=False)
-    if optimizer_name.lower() == "cobyla":
-        optimizer = COBYLA(maxiter=optimizer_max_iter, disp=True)
-    elif optimizer_name.lower() == "slsqp":
-        optimizer = SLSQP(maxiter=optimizer_max_iter, disp=True)
-    else:
-        raise ValueError(f"Invalid optimizer_name: {optimizer_name}")
-    if estimator is None:
-        estimator = _default_estimator()
-
-    if vector_b.ndim == 2:
-        vector_b = vector_b.flatten()
-
-    vqls = VQLS(estimator=estimator, ansatz=ansatz, optimizer=optimizer, sampler=None,
-                options={"use_overlap_test": False, "use_local_cost_function": False}, seed=seed)
-    res = vqls.solve(matrix_a, vector_b)
-
-    vqls_circuit = res.state
     from ..statevector import Statevector
 
-    vqls_solution_vector = np.real(Statevector(res.state).data)
-    quantum_solution = postprocess_solution(matrix_a=matrix_a, vector_b=vector_b, solution_x=vqls_solution_vector)
+    t0 = time.time()
+    np.set_printoptions(precision=3, suppress=True)  # process-wide, like the reference (:36)
+    n_data = int(np.log2(matrix_a.shape[0]))
+    rhs = np.ravel(vector_b) if np.ndim(vector_b) == 2 else vector_b
 
-    qc_basis = vqls_circuit.decompose(reps=10)
+    solver = VQLS(
+        estimator=estimator if estimator is not None else _default_estimator(),
+        ansatz=ansatz if ansatz is not None else RealAmplitudes(num_qubits=n_data, entanglement="full", reps=3, insert_barriers=False),
+        optimizer=_make_optimizer(optimizer_name, optimizer_max_iter),
+        sampler=None,
+        options={"use_overlap_test": False, "use_local_cost_function": False},  # global cost through Hadamard tests
+        seed=seed,
+    )
+    outcome = solver.solve(matrix_a, rhs)
+    circuit = outcome.state  # the ansatz bound to the optimal parameters
+
+    amplitudes = np.real(Statevector(circuit).data)  # RealAmplitudes: the imaginary parts are rounding noise
+    x = postprocess_solution(matrix_a=matrix_a, vector_b=rhs, solution_x=amplitudes)
+
+    leaves = circuit.decompose(reps=10)
     if show_circuit:
-        print(qc_basis)
-    qasm_content = circuit_to_qasm3(circuit=vqls_circuit, filename="vqls_qiskit_circuit.qasm3")
-    print(f"Comparing depths original {vqls_circuit.depth()} vs. decomposed {qc_basis.depth()}")
-
-    return (quantum_solution, qasm_content, qc_basis.depth(), vqls_circuit.width(), time.time() - start_time)
+        print(leaves)
+    qasm_text = utils.circuit_to_qasm3(circuit=circuit, filename=QASM_FILE)  # the reference exports the UN-decomposed circuit (:76-79)
+    print(f"Comparing depths original {circuit.depth()} vs. decomposed {leaves.depth()}")
+    return x, qasm_text, leaves.depth(), circuit.width(), time.time() - t0
 
 
 def postprocess_solution(matrix_a: np.ndarray, vector_b: np.ndarray, solution_x: np.ndarray) -> np.ndarray:
-    """Rescale the normalised VQLS state to a solution of ``Ax = b`` (norm of ``Ax`` vs ``b``), fix
-    the global sign (first component where ``Ax`` and ``b`` disagree in sign decides), and drop the
-    zero half of a Hermitian-embedded system (reference ``:94-126``)."""
-    lhs = np.matmul(matrix_a, solution_x)
-    scaled = solution_x * (np.linalg.norm(vector_b) / np.linalg.norm(lhs))
-    same_sign = True
-    for i in range(len(vector_b)):
-        li = lhs[i] if lhs.ndim == 1 else lhs[0, i]
-        same_sign = abs(vector_b[i]) + abs(li) == abs(vector_b[i] + li)
-        if not same_sign:
+    """From the unit vector VQLS returns to a solution of ``Ax = b`` (reference ``:94-126``):
+
+    * length: ``|b| / |A x|``;
+    * sign: walk the components of ``A x`` and ``b`` until one pair disagrees in sign
+      (``|b_i| + |(Ax)_i| != |b_i + (Ax)_i|``); if the LAST pair looked at disagrees, flip ``x``;
+    * a Hermitian-embedded system ``[[0, A], [A^H, 0]]`` keeps only the second half."""
+    image = np.asarray(np.matmul(matrix_a, solution_x))
+    row = image if image.ndim == 1 else image[0]
+    x = solution_x * (np.linalg.norm(vector_b) / np.linalg.norm(image))
+    agrees = True
+    for b_i, ax_i in zip(vector_b, row):
+        agrees = abs(b_i) + abs(ax_i) == abs(b_i + ax_i)
+        if not agrees:
             break
-    if not same_sign:
-        scaled = -scaled
-    if is_expanded(matrix_a, vector_b):
-        scaled = extract_x_from_expanded(scaled)
-    return scaled
+    if not agrees:
+        x = -x
+    return utils.extract_x_from_expanded(x) if utils.is_expanded(matrix_a, vector_b) else x
