@@ -54,14 +54,16 @@ def reciprocal_angle_by_value(nl: int, delta: float) -> np.ndarray:
         v, sign = c & (m - 1), c >> (nl - 1)
         if v == 0:
             continue
-        r = delta * m / v
-        if math.isclose(r, 1, abs_tol=1e-5):
-            th = math.pi
-        elif r < 1:
+        # sign = 0: the value bits read lambda ~ v/m;  sign = 1 (two's complement): lambda ~ -(1 - v/m)
+        lam = v / m if not sign else -(1.0 - v / m)
+        r = delta / lam
+        if math.isclose(abs(r), 1, abs_tol=1e-5):
+            th = math.copysign(math.pi, r)
+        elif abs(r) < 1:
             th = 2 * math.asin(r)
         else:
             th = 0.0
-        out[c] = -th if sign else th
+        out[c] = th
     return out
 
 

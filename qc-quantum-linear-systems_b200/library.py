@@ -114,13 +114,15 @@ def exact_reciprocal_angles(num_state_qubits: int, scaling: float, neg_vals: boo
             angles.append(2 * math.asin(r))
         else:
             angles.append(0.0)
+    # sign qubit set: QPE holds a negative eigenvalue in two's complement, i.e. the value bits i encode
+    # lambda ~ -(1 - i/nl); the rotation is by scaling / lambda  [qiskit ExactReciprocal, neg_vals branch]
     angles_neg = [0.0]
     for i in range(1, nl):
-        r = scaling * nl / i
-        if math.isclose(r, 1, abs_tol=1e-5):
+        r = scaling * (-1) / (1 - i / nl)
+        if math.isclose(r, -1, abs_tol=1e-5):
             angles_neg.append(-math.pi)
         elif abs(r) < 1:
-            angles_neg.append(-2 * math.asin(r))
+            angles_neg.append(2 * math.asin(r))
         else:
             angles_neg.append(0.0)
     return np.array(angles), np.array(angles_neg)

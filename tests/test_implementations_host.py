@@ -70,7 +70,10 @@ def test_solve_hhl_qiskit_toy_models(oracle_engine, model):
 
     x, _, _, width, _ = solve_hhl_qiskit(model.matrix_a, model.vector_b)
     assert x.shape == np.asarray(model.classical_solution).reshape(-1).shape
-    assert relative_distance_quantum_classical_solution(x, np.asarray(model.classical_solution).reshape(-1)) < 20.0
+    # the reference's gate normalises both vectors first (plotting.py:123-124, 136-143); ToyModel.normalize_model
+    # also rescales classical_solution although A and b are divided by the same factor (toymodels.py:59-64)
+    cs = np.asarray(model.classical_solution).reshape(-1)
+    assert relative_distance_quantum_classical_solution(x / np.linalg.norm(x), cs / np.linalg.norm(cs)) < 20.0
     assert width >= 2 * model.num_qubits + 2
 
 

@@ -81,6 +81,25 @@ def test_solution_quality_within_reference_gate():
         assert rel < bound, (model.name, rel)
 
 
+@pytest.mark.parametrize("matrix, vector", [
+    ([[0.0, 1.0], [1.0, 0.0]], [1.0, 0.0]),   # eigenvalues +-1: x = [0, 1]
+    ([[1.0, 2.0], [2.0, 1.0]], [1.0, 0.0]),   # eigenvalues 3, -1: x = [-1/3, 2/3]
+    ([[1.0, 2.0], [2.0, 1.0]], [0.6, -0.8]),
+])
+def test_negative_eigenvalues_solve_the_system_passed_in(matrix, vector):
+    """``ExactReciprocal(neg_vals=True)``: with the sign qubit set, QPE holds the eigenvalue in two's
+    complement and the second controlled UCRY rotates by ``scaling / -(1 - i/nl)``.  Both eigenvalues of
+    these matrices are exactly representable on the clock register, so HHL is exact: compare with
+    ``np.linalg.solve`` of the very system that was passed in (no model-side rescaling)."""
+    a, b = np.asarray(matrix), np.asarray(vector)
+    hhl = HHL(power_mode="repeat")
+    qc = hhl.construct_circuit(a, b)
+    psi = _oracle_state(qc)
+    assert np.max(np.abs(psi - hhl_analytic.hhl_state(a, b))) < 1e-12
+    x = numpy_sv.hhl_norm(psi, 2, hhl.scaling) * extract_hhl_solution_vector_from_state_vector(a, psi)
+    assert np.max(np.abs(x - np.linalg.solve(a, b / np.linalg.norm(b)))) < 1e-12
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_evolve_operator_matches_dense_unitary(seed):
     rng = np.random.default_rng(seed)
