@@ -156,6 +156,34 @@ int qls_program_destroy(QlsProgram* prog);
 int qls_program_run(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset, uint32_t pass_begin,
                     uint32_t pass_end, void* stream);
 
+/* ---- specialised pass kernels ----------------------------------------------------------------
+ * A pass with a register-stage form can be given a kernel compiled for exactly that pass (stage layouts,
+ * register indices, table-index fields and gate matrices as compile-time constants; qls_b200/jit.py
+ * writes the source, csrc/rs2_runtime.cuh + rs2_kernel.cuh are the skeleton: a producer warp moving
+ * tiles with bulk asynchronous copies, two consumer groups, three shared-memory tile buffers).
+ * qls_program_run launches it instead of the interpreter kernel.  [same call site, hhl..:49] */
+
+/* CUDA C++ -> sm_100a cubin with NVRTC (no GPU needed).  `header_names[i]` is what the source #includes,
+ * `header_sources[i]` its text.  *cubin_out is malloc'ed: release it with qls_jit_free.  The tail of the
+ * compiler log is copied to `log` (may be NULL). */
+int qls_jit_compile(const char* source, const char* const* header_names, const char* const* header_sources, int n_headers,
+                    const char* const* options, int n_options, void** cubin_out, uint64_t* cubin_bytes, char* log,
+                    uint64_t log_cap);
+int qls_jit_free(void* cubin);
+/* Attach `kernel_name` of the cubin to pass `pass_index` (block of `threads` threads, `smem_bytes` of dynamic
+ * shared memory; signature (state, index_offset, n_tiles, pool)). */
+int qls_program_set_pass_kernel(QlsProgram* prog, uint32_t pass_index, const void* cubin, uint64_t cubin_bytes,
+                                const char* kernel_name, uint32_t threads, uint32_t smem_bytes);
+/* The attached kernel lands its tiles with tensor-map copies (cp.async.bulk.tensor): describe the tile of the pass.
+ * Tile qubits [0, low_bits) are rows of 128 bytes (box dimensions 0 and 1); each of the n_groups <= 3 groups is
+ * group_bits[g] tile qubits at consecutive index bits from group_pos[g] (one box dimension each).  The map itself
+ * is encoded per launch (it holds the state pointer).  Without this call the kernel is expected to use per-run
+ * bulk copies. */
+int qls_program_set_pass_tma(QlsProgram* prog, uint32_t pass_index, int low_bits, int n_groups, const int* group_pos,
+                             const int* group_bits, int n_local);
+/* 1 (default): use attached specialised kernels; 0: always the interpreter kernels (A/B tests). */
+int qls_set_use_jit(int on);
+
 /* ---- state initialisation and host <-> device access ------------------------------------- */
 
 /* psi = 0; psi[basis_index] = 1 (pass UINT64_MAX to only zero).  [Statevector.from_instruction] */

@@ -106,6 +106,12 @@ SYMBOLS = {
                                 C.POINTER(_vp)]),
     "qls_set_sweep_only": (_i, [_i]),
     "qls_program_destroy": (_i, [_vp]),
+    "qls_jit_compile": (_i, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, C.POINTER(C.c_char_p), _i,
+                            C.POINTER(_vp), C.POINTER(_u64), C.c_char_p, _u64]),
+    "qls_jit_free": (_i, [_vp]),
+    "qls_program_set_pass_kernel": (_i, [_vp, _u32, _vp, _u64, C.c_char_p, _u32, _u32]),
+    "qls_program_set_pass_tma": (_i, [_vp, _u32, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i]),
+    "qls_set_use_jit": (_i, [_i]),
     "qls_program_run": (_i, [_vp, _vp, _i, _u64, _u32, _u32, _vp]),
     "qls_sv_init_basis": (_i, [_vp, _i, _i, _u64, _vp]),
     "qls_sv_write": (_i, [_vp, _i, _u64, _vp, _u64, _vp]),

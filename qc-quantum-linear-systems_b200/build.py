@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libqls_b200.so")
-SOURCES = ["state_ops.cu", "tile_pass.cu", "rs_pass.cu", "ctrl_gemm.cu", "batch_sv.cu", "remap.cu"]
+SOURCES = ["state_ops.cu", "tile_pass.cu", "rs_pass.cu", "ctrl_gemm.cu", "batch_sv.cu", "remap.cu", "jit.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or not _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         subprocess.run(cmd, check=True)
     return LIB
 

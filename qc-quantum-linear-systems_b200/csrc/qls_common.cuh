@@ -44,6 +44,8 @@ struct QlsProgram {
   uint64_t* rs_img_off;    // [n_passes] byte offset into rs_img_dev
   uint32_t* rs_img_bytes;  // [n_passes] 0: the pass has no register-stage form
   uint8_t* rs_img_kr;      // [n_passes] register qubits per thread of the pass's stages (4 or 5)
+  // specialised (NVRTC-compiled) kernels, one per pass that has one; nullptr: none attached (jit.cu)
+  struct QlsJitKernel** jit;
 };
 
 // register-stage fast path (rs_pass.cu)
@@ -51,6 +53,12 @@ int qls_rs_build_images(QlsProgram* prog, const QlsRsOp* rs_ops_host, const unsi
 bool qls_rs_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, int n_local);
 int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
                        uint64_t index_offset, cudaStream_t stream);
+
+// specialised pass kernels (jit.cu)
+void qls_jit_release(QlsProgram* prog);
+bool qls_jit_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, int n_local);
+int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
+                        uint64_t index_offset, cudaStream_t stream);
 
 // ---- complex arithmetic on double2 / float2 -----------------------------------------------------
 template <typename R>

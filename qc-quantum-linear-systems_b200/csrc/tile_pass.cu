@@ -126,6 +126,12 @@ extern "C" int qls_set_sweep_only(int on) {
   return QLS_OK;
 }
 
+static int g_use_jit = 1;
+extern "C" int qls_set_use_jit(int on) {
+  g_use_jit = on ? 1 : 0;
+  return QLS_OK;
+}
+
 extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset,
                                uint32_t pass_begin, uint32_t pass_end, void* stream) {
   QLS_ARG(prog && state, "null program or state");
@@ -138,6 +144,11 @@ extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local,
     int rc = validate_pass(p, n_local, prog->dtype);
     if (rc) return rc;
     QLS_ARG(!(p.pad & 4u), "pass %u holds batch-only ops (PARAM / MATVEC): use qls_batch_expect_z", i);
+    if (!g_sweep_only && g_use_jit && qls_jit_eligible(prog, p, i, n_local)) {
+      rc = qls_launch_jit_pass(prog, p, i, state, n_local, index_offset, s);
+      if (rc) return rc;
+      continue;
+    }
     if (!g_sweep_only && qls_rs_eligible(prog, p, i, n_local)) {
       rc = qls_launch_rs_pass(prog, p, i, state, n_local, index_offset, s);
       if (rc) return rc;
@@ -204,6 +215,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   p->rs_img_off = nullptr;
   p->rs_img_bytes = nullptr;
   p->rs_img_kr = nullptr;
+  p->jit = nullptr;
   for (uint32_t i = 0; i < n_passes; ++i) {
     p->passes_host[i] = passes_host[i];
     QlsPass& ps = p->passes_host[i];
@@ -279,6 +291,7 @@ extern "C" int qls_program_destroy(QlsProgram* prog) {
   if (prog->rs_ops_dev) cudaFree(prog->rs_ops_dev);
   if (prog->pool_dev) cudaFree(prog->pool_dev);
   if (prog->rs_img_dev) cudaFree(prog->rs_img_dev);
+  qls_jit_release(prog);
   delete[] prog->rs_img_off;
   delete[] prog->rs_img_bytes;
   delete[] prog->rs_img_kr;

@@ -133,6 +133,19 @@ class DeviceProgram:
                                                    lowered.n_rs_ops, pool.ctypes.data, pool.size,
                                                    self.abi_dtype, self.device, C.byref(handle)))
         self.handle = handle
+        # Specialised kernels: every pass with a register-stage form gets a kernel compiled for exactly that pass
+        # (qls_b200/jit.py; NVRTC through the C ABI, cubins cached on disk).  A failure is an error, not a silent
+        # fall-back to the interpreter kernels; QLS_JIT=0 selects those on purpose.
+        self.jit_passes = 0
+        self.jit_modes = {}
+        from . import jit
+
+        if jit.enabled() and lowered.dtype == "fp64" and lowered.n_local >= jit.min_qubits():
+            with torch.cuda.device(self.device):
+                for cp in jit.compile_program(lowered):
+                    mode = jit.attach(self.lib, self.handle, cp, lowered.n_local)
+                    self.jit_passes += 1
+                    self.jit_modes[mode] = self.jit_modes.get(mode, 0) + 1
         self._gemm_mats = {}
         cdt = torch.complex128 if lowered.dtype == "fp64" else torch.complex64
         for i, s in enumerate(lowered.steps):

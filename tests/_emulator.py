@@ -244,7 +244,13 @@ def run_program(lowered, psi0=None, index_offset=0, params=None, form="sweep"):
         if s.kind == "passes":
             for pi in range(s.pass_begin, s.pass_end):
                 ps = lowered.passes[pi]
-                if form == "rs" and ps.rs_count > 0:
+                if form == "jit" and ps.rs_count > 0:
+                    # the generated (specialised) source, compiled for the host: tests/_jit_emu.py
+                    import _jit_emu
+
+                    if not _jit_emu.run_pass(state, lowered, pi, n, index_offset):
+                        run_pass_rs(state, ps, lowered.rs_ops, pool, cdtype, n, index_offset)
+                elif form in ("rs", "jit") and ps.rs_count > 0:
                     run_pass_rs(state, ps, lowered.rs_ops, pool, cdtype, n, index_offset)
                 else:
                     run_pass(state, ps, lowered.ops, pool, cdtype, n, index_offset, params)
