@@ -181,6 +181,9 @@ int qls_program_set_pass_kernel(QlsProgram* prog, uint32_t pass_index, const voi
  * bulk copies. */
 int qls_program_set_pass_tma(QlsProgram* prog, uint32_t pass_index, int low_bits, int n_groups, const int* group_pos,
                              const int* group_bits, int n_local);
+/* Debug: device buffer (>= 16 + 16 * 8192 bytes, zeroed) that kernels compiled with -DQLS_TRACE fill with the
+ * timeline of CTA 0 (tools/jit_trace.py); NULL (default) switches it off. */
+int qls_set_trace_buffer(void* trace_dev);
 /* 1 (default): use attached specialised kernels; 0: always the interpreter kernels (A/B tests). */
 int qls_set_use_jit(int on);
 

@@ -112,6 +112,7 @@ SYMBOLS = {
     "qls_program_set_pass_kernel": (_i, [_vp, _u32, _vp, _u64, C.c_char_p, _u32, _u32]),
     "qls_program_set_pass_tma": (_i, [_vp, _u32, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i]),
     "qls_set_use_jit": (_i, [_i]),
+    "qls_set_trace_buffer": (_i, [_vp]),
     "qls_program_run": (_i, [_vp, _vp, _i, _u64, _u32, _u32, _vp]),
     "qls_sv_init_basis": (_i, [_vp, _i, _i, _u64, _vp]),
     "qls_sv_write": (_i, [_vp, _i, _u64, _vp, _u64, _vp]),

@@ -266,6 +266,12 @@ extern "C" int qls_program_set_pass_tma(QlsProgram* prog, uint32_t pass_index, i
   return rc;
 }
 
+static void* g_trace_dev = nullptr;
+extern "C" int qls_set_trace_buffer(void* trace_dev) {
+  g_trace_dev = trace_dev;
+  return QLS_OK;
+}
+
 void qls_jit_release(QlsProgram* prog) {
   if (!prog->jit) return;
   Driver* d = driver();
@@ -302,7 +308,8 @@ int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_
     const int erc = qls_encode_tile_map(d, k, state, n_local, &tmap);
     if (erc) return erc;
   }
-  void* args[] = {&state, &index_offset, &n_tiles, &pool, &tmap};
+  void* trace = g_trace_dev;
+  void* args[] = {&state, &index_offset, &n_tiles, &pool, &tmap, &trace};
   const int rc = d->LaunchKernel(k->fn, (unsigned)grid, 1, 1, k->threads, 1, 1, k->smem, stream, args, nullptr);
   if (rc) {
     qls_set_error("cuLaunchKernel (pass %u): %s", pass_index, cu_err(d, rc));

@@ -27,20 +27,22 @@ static_assert(QLS_GROUPS * QLS_GROUP_THREADS * QLS_CONSUMER_REGS + 128 * 24 <= Q
 
 extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
     qls_rs2_pass(V* __restrict__ state, const u64 index_offset, const u64 n_tiles, const unsigned char* __restrict__ pool,
-                 const __grid_constant__ QlsTensorMap tmap) {
+                 const __grid_constant__ QlsTensorMap tmap, u64* __restrict__ qls_trace) {
   extern __shared__ unsigned char qls_smem_raw[];
   // 1024-byte alignment: the tensor-map swizzle pattern is a function of the shared-memory address
   unsigned char* const qls_smem = qls_smem_raw + ((1024u - (qls_smem_u32(qls_smem_raw) & 1023u)) & 1023u);
   u64* full = reinterpret_cast<u64*>(qls_smem + QLS_NBUF * QLS_BUF_BYTES);  // [QLS_NBUF] tile has landed (producer -> groups)
   u64* done = full + QLS_NBUF;                                              // [QLS_NBUF] tile is finished (group -> producer)
-  volatile u32* ctl = reinterpret_cast<volatile u32*>(done + QLS_NBUF);     // [0] ticket counter, [1 + g] ticket of group g
+  volatile u32* ctl = reinterpret_cast<volatile u32*>(done + QLS_NBUF);     // [0] ticket counter, [1 + g] ticket of group g,
+                                                                            // [4 + b] ordinal + 1 of the tile buffer b is armed for,
+                                                                            // [8 + who] trace cursor (debug builds)
   const u32 warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   if (threadIdx.x == 0) {
     for (int b = 0; b < QLS_NBUF; ++b) {
       qls_mbar_init(full + b, 1);
       qls_mbar_init(done + b, 1);
     }
-    ctl[0] = 0;
+    for (int j = 0; j < 12; ++j) ctl[j] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -51,9 +53,16 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
     if (warp != QLS_GROUPS * (QLS_GROUP_THREADS / 32)) return;
     // ===== producer warp: bulk copies in, bulk copies out =====
     const u32 lane = threadIdx.x & 31u;
+#ifdef QLS_TRACE
+#define QLS_PTR(ev, qq) do { if (lane == 0) qls_trace_put(qls_trace, ctl + 8, 2u, (ev), (u32)(qq)); } while (0)
+#else
+#define QLS_PTR(ev, qq) do { } while (0)
+#endif
     auto retire = [&](u64 qq) {  // tile qq is finished: write it back and free its buffer
       const u32 b = (u32)(qq % QLS_NBUF);
+      QLS_PTR(20, qq);
       qls_mbar_wait(done + b, (u32)(qq / QLS_NBUF) & 1u);
+      QLS_PTR(21, qq);
       const u64 base = qls_tile_base((u64)blockIdx.x + qq * gridDim.x);
       if (!qls_tile_idle(base | index_offset)) {
         unsigned char* buf = qls_smem + b * QLS_BUF_BYTES;
@@ -68,6 +77,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
         qls_bulk_wait_read();  // the buffer may be overwritten once the copy engine has read it
       }
       __syncwarp();
+      QLS_PTR(22, qq);
     };
     u64 q = 0;
     for (;; ++q) {
@@ -78,6 +88,11 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       const u64 base = qls_tile_base(tile);
       const bool idle = qls_tile_idle(base | index_offset);
       if (lane == 0) {
+        // Publish which tile this round of the buffer belongs to BEFORE arming it.  A parity wait cannot tell round
+        // R + 2 from round R: a group that runs two tiles ahead of a load still in flight (tiles land out of order)
+        // would otherwise take the buffer of a tile that has not landed.
+        ctl[4 + b] = (u32)q + 1u;
+        __threadfence_block();
         if (idle) qls_mbar_arrive(full + b);  // nothing to move: the group only passes the tile through
         else qls_mbar_arrive_expect_tx(full + b, QLS_TILE_BYTES);
       }
@@ -92,6 +107,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
           qls_bulk_load(buf + qls_land_bytes(r), state + (base | qls_run_offset(r)), QLS_RUN_BYTES, full + b);
 #endif
       }
+      QLS_PTR(23, q);
     }
     for (u64 qq = q >= QLS_NBUF ? q - QLS_NBUF : 0; qq < q; ++qq) retire(qq);
     qls_bulk_wait_all();
@@ -104,17 +120,30 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       if (tid == 0) ctl[1 + qls_group] = atomicAdd(const_cast<u32*>(&ctl[0]), 1u);
       QLS_BAR();
       const u32 q = ctl[1 + qls_group];
+      const u32 qls_q = q;
+      volatile u32* const qls_cursor = ctl + 8;
+      (void)qls_cursor;
       const u64 tile = (u64)blockIdx.x + (u64)q * gridDim.x;
       if (tile >= n_tiles) break;
       const u32 b = q % QLS_NBUF;
+      QLS_TR(1);
+      {  // the buffer must be armed for THIS tile (see the producer) before the parity of its barrier means anything
+        u32 spins = 0;
+        while (ctl[4 + b] != q + 1u) {
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
       qls_mbar_wait(full + b, (q / QLS_NBUF) & 1u);
+      QLS_TR(2);
       const u64 gbase = qls_tile_base(tile) | index_offset;
       if (!qls_tile_idle(gbase)) {
-        qls_tile_body(reinterpret_cast<V*>(qls_smem + b * QLS_BUF_BYTES), gbase, tid, qls_group, pool);
+        qls_tile_body(reinterpret_cast<V*>(qls_smem + b * QLS_BUF_BYTES), gbase, tid, qls_group, pool, qls_trace, qls_q, qls_cursor);
         qls_fence_proxy_async();  // the bulk store reads this group's shared-memory writes through the async proxy
       }
+      QLS_TR(3);
       QLS_BAR();
       if (tid == 0) qls_mbar_arrive(done + b);
+      QLS_TR(4);
     }
   }
 }
@@ -136,7 +165,7 @@ extern "C" void qls_emu_run_pass(V* state, u64 index_offset, u64 n_tiles, const 
       },
       [&](u64 tile, u32 tid) {
         const u64 gbase = qls_tile_base(tile) | index_offset;
-        if (!qls_tile_idle(gbase)) qls_tile_body(buf, gbase, tid, 0u, pool);
+        if (!qls_tile_idle(gbase)) qls_tile_body(buf, gbase, tid, 0u, pool, nullptr, 0u, nullptr);
       });
 }
 

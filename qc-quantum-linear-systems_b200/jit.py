@@ -35,7 +35,7 @@ KERNEL_NAME = "qls_rs2_pass"
 T = 12  # tile bits of the specialised kernels (complex128)
 KR = 4  # register qubits per thread
 THREADS = 2 * 256 + 128  # two consumer groups + the producer warpgroup
-GEN_VERSION = 6  # bump when the generated code or the runtime headers change meaning
+GEN_VERSION = 8  # bump when the generated code or the runtime headers change meaning
 
 
 # --------------------------------------------------------------------------------------
@@ -504,8 +504,10 @@ class _Gen:
                     ind -= 1
                     self.emit("}", ind)
             self.emit(f"cur = {s};", ind)
+            self.emit(f"QLS_TR({10 + 2 * s});", ind)
             for op in st.ops:
                 self._emit_op(s, op, ind)
+            self.emit(f"QLS_TR({11 + 2 * s});", ind)
             if fire:
                 self.emit("}")
         # write back in the landing layout
@@ -567,8 +569,9 @@ class _Gen:
             out.append("  return !(" + " || ".join(self.preds.values()) + ");")
         out.append("}")
         out.append("QLS_DEV void qls_tile_body(V* __restrict__ sm, const u64 gbase, const u32 tid, const u32 qls_group,")
-        out.append("                           const unsigned char* __restrict__ pool) {")
-        out.append("  (void)qls_group; (void)pool;")
+        out.append("                           const unsigned char* __restrict__ pool, u64* qls_trace, const u32 qls_q,")
+        out.append("                           volatile u32* qls_cursor) {")
+        out.append("  (void)qls_group; (void)pool; (void)qls_trace; (void)qls_q; (void)qls_cursor;")
         out.append("  V " + ", ".join(f"a{r}" for r in range(2**KR)) + ";")
         out.append("  int cur = -1;")
         out.append("  bool landed = false;")
@@ -585,7 +588,7 @@ def generate_source(jp: JPass, mode: Optional[str] = None) -> str:
 
 def smem_bytes(jp: JPass, mode: Optional[str] = None) -> int:
     buf = (Layout(jp.L, jp.high, mode).land_units() * 16 + 1023) & ~1023
-    return 3 * buf + 2 * 3 * 8 + 16 + 1024  # + slack to align the buffers to 1024 bytes (tensor-map swizzle)
+    return 3 * buf + 2 * 3 * 8 + 64 + 1024  # + slack to align the buffers to 1024 bytes (tensor-map swizzle)
 
 
 def tma_descriptor(jp: JPass, mode: Optional[str] = None):
@@ -611,6 +614,8 @@ def _headers() -> Dict[str, str]:
 
 
 NVRTC_OPTIONS = ["--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"]
+if os.environ.get("QLS_JIT_TRACE", "0") != "0":  # timeline of CTA 0 (tools/jit_trace.py); never set in production
+    NVRTC_OPTIONS.append("-DQLS_TRACE")
 
 
 def cache_key(source: str) -> str:
