@@ -166,7 +166,8 @@ int qls_program_run(const QlsProgram* prog, void* state, int n_local, uint64_t i
 /* CUDA C++ -> sm_100a cubin with NVRTC (no GPU needed).  `header_names[i]` is what the source #includes,
  * `header_sources[i]` its text.  *cubin_out is malloc'ed: release it with qls_jit_free.  The tail of the
  * compiler log is copied to `log` (may be NULL). */
-int qls_jit_compile(const char* source, const char* const* header_names, const char* const* header_sources, int n_headers,
+int qls_jit_compile(const char* source, const char* source_name /* file name in the line table; may be NULL */,
+                    const char* const* header_names, const char* const* header_sources, int n_headers,
                     const char* const* options, int n_options, void** cubin_out, uint64_t* cubin_bytes, char* log,
                     uint64_t log_cap);
 int qls_jit_free(void* cubin);

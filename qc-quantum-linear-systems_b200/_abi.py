@@ -106,7 +106,7 @@ SYMBOLS = {
                                 C.POINTER(_vp)]),
     "qls_set_sweep_only": (_i, [_i]),
     "qls_program_destroy": (_i, [_vp]),
-    "qls_jit_compile": (_i, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, C.POINTER(C.c_char_p), _i,
+    "qls_jit_compile": (_i, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, C.POINTER(C.c_char_p), _i,
                             C.POINTER(_vp), C.POINTER(_u64), C.c_char_p, _u64]),
     "qls_jit_free": (_i, [_vp]),
     "qls_program_set_pass_kernel": (_i, [_vp, _u32, _vp, _u64, C.c_char_p, _u32, _u32]),

@@ -141,9 +141,9 @@ static int qls_encode_tile_map(Driver* d, const QlsJitKernel* k, void* state, in
   return QLS_OK;
 }
 
-extern "C" int qls_jit_compile(const char* source, const char* const* header_names, const char* const* header_sources,
-                               int n_headers, const char* const* options, int n_options, void** cubin_out,
-                               uint64_t* cubin_bytes, char* log, uint64_t log_cap) {
+extern "C" int qls_jit_compile(const char* source, const char* source_name, const char* const* header_names,
+                               const char* const* header_sources, int n_headers, const char* const* options, int n_options,
+                               void** cubin_out, uint64_t* cubin_bytes, char* log, uint64_t log_cap) {
   QLS_ARG(source && cubin_out && cubin_bytes, "null pointer");
   if (log && log_cap) log[0] = 0;
   Nvrtc* n = nvrtc();
@@ -152,7 +152,7 @@ extern "C" int qls_jit_compile(const char* source, const char* const* header_nam
     return QLS_ERR_UNSUPPORTED;
   }
   nvrtcProgram prog = nullptr;
-  int rc = n->CreateProgram(&prog, source, "qls_pass.cu", n_headers, header_sources, header_names);
+  int rc = n->CreateProgram(&prog, source, source_name && *source_name ? source_name : "qls_pass.cu", n_headers, header_sources, header_names);
   if (rc) {
     qls_set_error("nvrtcCreateProgram: %s", n->GetErrorString ? n->GetErrorString(rc) : "?");
     return QLS_ERR_CUDA;

@@ -18,6 +18,8 @@ struct double2 {
 };
 #define QLS_DEV static inline
 #define QLS_CONST static const
+#define QLS_UNIFORM(x) (x)
+#define QLS_FRESH_TID(k) (tid_in | (u32)(gbase >> (42 + (k))))
 template <class T>
 static inline T __ldg(const T* p) {
   return *p;
@@ -26,6 +28,7 @@ using std::fma;
 
 static pthread_barrier_t qls_emu_bar;
 #define QLS_BAR() pthread_barrier_wait(&qls_emu_bar)
+#define QLS_BODY_BAR() QLS_BAR()
 
 template <class Copy, class Body>
 static void qls_emu_run(u64 n_tiles, Copy copy, Body body) {

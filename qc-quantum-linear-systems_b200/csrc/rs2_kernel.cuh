@@ -33,8 +33,8 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
   unsigned char* const qls_smem = qls_smem_raw + ((1024u - (qls_smem_u32(qls_smem_raw) & 1023u)) & 1023u);
   u64* full = reinterpret_cast<u64*>(qls_smem + QLS_NBUF * QLS_BUF_BYTES);  // [QLS_NBUF] tile has landed (producer -> groups)
   u64* done = full + QLS_NBUF;                                              // [QLS_NBUF] tile is finished (group -> producer)
-  volatile u32* ctl = reinterpret_cast<volatile u32*>(done + QLS_NBUF);     // [0] ticket counter, [1 + g] ticket of group g,
-                                                                            // [4 + b] ordinal + 1 of the tile buffer b is armed for,
+  volatile u32* ctl = reinterpret_cast<volatile u32*>(done + QLS_NBUF);     // [0] ticket counter, [1 + 2 g + parity] ticket of group g,
+                                                                            // [5 + b] ordinal + 1 of the tile buffer b is armed for,
                                                                             // [8 + who] trace cursor (debug builds)
   const u32 warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   if (threadIdx.x == 0) {
@@ -66,7 +66,8 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       const u64 base = qls_tile_base((u64)blockIdx.x + qq * gridDim.x);
       if (!qls_tile_idle(base | index_offset)) {
         unsigned char* buf = qls_smem + b * QLS_BUF_BYTES;
-#ifdef QLS_TMA
+#ifdef QLS_EXP_NOLOAD  // timing experiment: no global traffic at all
+#elif defined(QLS_TMA)
         if (lane < QLS_TMA_OPS)
           qls_tma_store(&tmap, (u32)((base | qls_tma_split_offset(lane)) >> 3), buf + lane * (QLS_TILE_BYTES / QLS_TMA_OPS));
 #else
@@ -91,15 +92,20 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
         // Publish which tile this round of the buffer belongs to BEFORE arming it.  A parity wait cannot tell round
         // R + 2 from round R: a group that runs two tiles ahead of a load still in flight (tiles land out of order)
         // would otherwise take the buffer of a tile that has not landed.
-        ctl[4 + b] = (u32)q + 1u;
+        ctl[5 + b] = (u32)q + 1u;
         __threadfence_block();
+#ifdef QLS_EXP_NOLOAD
+        qls_mbar_arrive(full + b);
+#else
         if (idle) qls_mbar_arrive(full + b);  // nothing to move: the group only passes the tile through
         else qls_mbar_arrive_expect_tx(full + b, QLS_TILE_BYTES);
+#endif
       }
       __syncwarp();
       if (!idle) {
         unsigned char* buf = qls_smem + b * QLS_BUF_BYTES;
-#ifdef QLS_TMA
+#ifdef QLS_EXP_NOLOAD
+#elif defined(QLS_TMA)
         if (lane < QLS_TMA_OPS)
           qls_tma_load(buf + lane * (QLS_TILE_BYTES / QLS_TMA_OPS), &tmap, (u32)((base | qls_tma_split_offset(lane)) >> 3), full + b);
 #else
@@ -116,10 +122,18 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 " QLS_STR(QLS_CONSUMER_REGS) ";");
     const u32 qls_group = warp / (QLS_GROUP_THREADS / 32);
     const u32 tid = threadIdx.x & (QLS_GROUP_THREADS - 1);
-    for (;;) {
-      if (tid == 0) ctl[1 + qls_group] = atomicAdd(const_cast<u32*>(&ctl[0]), 1u);
-      QLS_BAR();
-      const u32 q = ctl[1 + qls_group];
+#ifdef QLS_EXP_ONEGROUP  // timing experiment: the second group does nothing
+    if (qls_group == 1) return;
+#endif
+    // Tickets: thread 0 of a group draws the ordinal of the group's NEXT tile before the barrier that ends the current
+    // one, so that barrier publishes it (no barrier of its own).  Two slots per group, alternating: a warp that is
+    // slow to read the current ordinal is at most one barrier behind the writer.
+    if (tid == 0) ctl[1 + 2 * qls_group] = atomicAdd(const_cast<u32*>(&ctl[0]), 1u);
+    QLS_BAR();
+    for (u32 it = 0;; ++it) {
+      // (the shuffle makes the ordinal provably warp-uniform: tile base and control predicates then live in uniform
+      // registers / uniform predicates instead of being spilled as per-thread booleans)
+      const u32 q = __shfl_sync(0xffffffffu, ctl[1 + 2 * qls_group + (it & 1u)], 0);
       const u32 qls_q = q;
       volatile u32* const qls_cursor = ctl + 8;
       (void)qls_cursor;
@@ -129,7 +143,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       QLS_TR(1);
       {  // the buffer must be armed for THIS tile (see the producer) before the parity of its barrier means anything
         u32 spins = 0;
-        while (ctl[4 + b] != q + 1u) {
+        while (ctl[5 + b] != q + 1u) {
           if (++spins > (1u << 26)) __trap();
         }
       }
@@ -141,6 +155,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
         qls_fence_proxy_async();  // the bulk store reads this group's shared-memory writes through the async proxy
       }
       QLS_TR(3);
+      if (tid == 0) ctl[1 + 2 * qls_group + ((it + 1u) & 1u)] = atomicAdd(const_cast<u32*>(&ctl[0]), 1u);
       QLS_BAR();
       if (tid == 0) qls_mbar_arrive(done + b);
       QLS_TR(4);

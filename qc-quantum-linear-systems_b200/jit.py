@@ -35,7 +35,7 @@ KERNEL_NAME = "qls_rs2_pass"
 T = 12  # tile bits of the specialised kernels (complex128)
 KR = 4  # register qubits per thread
 THREADS = 2 * 256 + 128  # two consumer groups + the producer warpgroup
-GEN_VERSION = 8  # bump when the generated code or the runtime headers change meaning
+GEN_VERSION = 21  # bump when the generated code or the runtime headers change meaning
 
 
 # --------------------------------------------------------------------------------------
@@ -325,6 +325,10 @@ def _hexf(x: float) -> str:
 # --------------------------------------------------------------------------------------
 
 
+class _TooBig(Exception):
+    pass
+
+
 class _Gen:
     def __init__(self, jp: JPass, mode: Optional[str] = None):
         self.jp = jp
@@ -333,6 +337,21 @@ class _Gen:
         self.lines: List[str] = []
         self.preds: Dict[Tuple[int, int], str] = {}  # external-control predicate -> variable
         self.lay = Layout(jp.L, jp.high, mode)
+        # QLS_JIT_SHAPES=1 (default 0): the 4x4 gates become steps of a small tile program whose switch cases are the
+        # distinct gate SHAPES of the pass, so that their code exists once.  Motivation: the straight-line form of a heavy
+        # pass is ~80 KB of code, more than twice the instruction cache of an SM, streamed by both consumer groups at
+        # different places (measured: GPC-level instruction cache at 78-89 % of its request rate, FP64 pipe 62-65 % active).
+        # Measured at n = 33: the program form is SLOWER (1044 vs 944 ms per solve) -- a dispatch per step and no
+        # scheduling across gates cost more than the instruction fetches saved -- so it stays an experiment.
+        est = 400
+        for st in jp.stages:
+            est += 120
+            for op in st.ops:
+                est += {"g2": 140 if op.real else 280, "g1": 40 if op.real else 72}.get(op.kind, 110)
+        self.share = os.environ.get("QLS_JIT_SHAPES", "0") != "0" and est > int(os.environ.get("QLS_JIT_SHARE_MIN", "2300"))
+        self.shapes: Dict[tuple, Tuple[int, List[str]]] = {}
+        self.steps: List[tuple] = []
+        self.chunk: List[str] = []
         self.orders = [choose_thread_order(s.regq, self.lay) for s in jp.stages]
 
     # -- per-stage address pieces ----------------------------------------------------------
@@ -346,6 +365,11 @@ class _Gen:
 
     def emit(self, line: str = "", ind: int = 1) -> None:
         self.lines.append("  " * ind + line)
+
+    def _flush_chunk(self) -> None:
+        if self.share and self.lines:
+            self.steps.append(("chunk", list(self.lines)))
+            del self.lines[:]
 
     def _landing(self, s: int, store: bool, ind: int) -> None:
         order = self.orders[s]
@@ -405,10 +429,35 @@ class _Gen:
         self.emit(f"const V* const tab = reinterpret_cast<const V*>(pool + {op.pool_off}ull) + ({idx});", ind)
         return [sum(((r >> j) & 1) << b for j, b in rbits) for r in range(2**KR)]
 
+    def _g_lines(self, k: int, real: bool, regs: Sequence[int], rm: int, rv: int, mexpr: str) -> List[str]:
+        fn = f"qls_g{k}{'r' if real else 'c'}"
+        rest = [j for j in range(KR) if j not in regs]
+        out = []
+        for g in range(2 ** (KR - k)):
+            i0 = sum(((g >> n) & 1) << rest[n] for n in range(len(rest)))
+            if (i0 & rm) != rv:
+                continue
+            args = [f"a{i0 | sum(((c >> j) & 1) << regs[j] for j in range(k))}" for c in range(2**k)]
+            out.append(f"{fn}({', '.join(args)}, {mexpr});")
+        return out
+
     def _emit_op(self, s: int, op: JOp, ind: int) -> None:
         regq = self.jp.stages[s].regq
         tm, tv, rm, rv = self._split_ctl(s, op)
         pred = self._pred(op)
+        if op.kind == "g2" and self.share:
+            # a step of the tile program: the code of a (targets, real/complex, register controls) shape exists once
+            k = len(op.targets)
+            moff = len(self.cm)
+            self.cm += [complex(v) for v in op.matrix.reshape(-1)]
+            regs = tuple(regq.index(t) for t in op.targets)
+            key = (k, op.real, regs, rm, rv)
+            if key not in self.shapes:
+                self.shapes[key] = (len(self.shapes), self._g_lines(k, op.real, regs, rm, rv, "M"))
+            self._flush_chunk()
+            pi = 255 if pred is None else int(pred[1:])
+            self.steps.append(("g", self.shapes[key][0], moff, pi, tm, tv))
+            return
         conds = ([pred] if pred else []) + ([f"(tid & {tm:#x}u) == {tv:#x}u"] if tm else [])
         if conds:
             self.emit("if (" + " && ".join(conds) + ") {", ind)
@@ -420,14 +469,8 @@ class _Gen:
             moff = len(self.cm)
             self.cm += [complex(v) for v in op.matrix.reshape(-1)]
             regs = [regq.index(t) for t in op.targets]
-            fn = f"qls_g{k}{'r' if op.real else 'c'}"
-            rest = [j for j in range(KR) if j not in regs]
-            for g in range(2 ** (KR - k)):
-                i0 = sum(((g >> n) & 1) << rest[n] for n in range(len(rest)))
-                if (i0 & rm) != rv:
-                    continue
-                args = [f"a{i0 | sum(((c >> j) & 1) << regs[j] for j in range(k))}" for c in range(2**k)]
-                self.emit(f"{fn}({', '.join(args)}, qls_cm + {moff});", ind)
+            for line in self._g_lines(k, op.real, regs, rm, rv, f"qls_cm + {moff}"):
+                self.emit(line, ind)
         elif op.kind == "diag":
             rt = self._table_index(s, op, ind)
             todo = [r for r in range(2**KR) if (r & rm) == rv]
@@ -468,60 +511,69 @@ class _Gen:
         always = [any(not op.xc_mask for op in st.ops) for st in jp.stages]
         body: List[str] = []
         self.lines = body
-        # possible values of `cur` on entry to stage s: the stages after the last one that always fires
+        # Every stage block: (enter) landing read if it is the first stage that fires on this tile, else read the
+        # exchange image; (ops); (leave) if a later stage fires on this tile, write the exchange image, else write the
+        # landing image.  Each piece of movement code exists once per stage; which one runs is decided by uniform
+        # predicates on the tile's control qubits.
+        fires = [None if always[s] else " || ".join(sorted({self._pred(op) for op in st.ops})) for s, st in enumerate(jp.stages)]
         for s, st in enumerate(jp.stages):
-            fire = None if always[s] else " || ".join(sorted({self._pred(op) for op in st.ops}))
+            fire = fires[s]
             ind = 1
             self.emit(f"// ---- stage {s}: register qubits at tile positions {list(st.regq)}, thread bits {self.orders[s]}")
             if fire:
                 self.emit(f"if ({fire}) {{")
                 ind = 2
-            last_always = max([j for j in range(s) if always[j]], default=-1)
-            cands = list(range(max(last_always, 0), s))
-            may_be_first = last_always < 0
+            may_be_first = not any(always[:s])
             if s == 0:
                 self._landing(0, False, ind)
                 self.emit("landed = true;", ind)
+            elif may_be_first:
+                self.emit("if (!loaded) {", ind)
+                self._landing(s, False, ind + 1)
+                self.emit("landed = true;", ind + 1)
+                self.emit("} else {", ind)
+                self._exchange(s, False, ind + 1)
+                self.emit("landed = false;", ind + 1)
+                self.emit("}", ind)
             else:
-                if may_be_first:
-                    self.emit("if (cur < 0) {", ind)
-                    self._landing(s, False, ind + 1)
-                    self.emit("landed = true;", ind + 1)
-                    self.emit("} else {", ind)
-                    ind += 1
-                self.emit("if (landed) QLS_BAR();  // the landing image has been read by everyone", ind)
-                for n, j in enumerate(cands):
-                    if len(cands) > 1:
-                        self.emit(("if" if n == 0 else "else if") + f" (cur == {j}) {{" if n < len(cands) - 1 else "else {", ind)
-                        self._exchange(j, True, ind + 1)
-                        self.emit("}", ind)
-                    else:
-                        self._exchange(j, True, ind)
-                self.emit("QLS_BAR();", ind)
                 self._exchange(s, False, ind)
                 self.emit("landed = false;", ind)
-                if may_be_first:
-                    ind -= 1
-                    self.emit("}", ind)
-            self.emit(f"cur = {s};", ind)
+            self.emit("loaded = true;", ind)
             self.emit(f"QLS_TR({10 + 2 * s});", ind)
+            if self.share and fire:  # the ops are steps of their own (each with its predicate): close the block here ...
+                self.emit("}")
             for op in st.ops:
-                self._emit_op(s, op, ind)
+                self._emit_op(s, op, 1 if self.share else ind)
+            if self.share and fire:  # ... and reopen it for the code that leaves the stage
+                self.emit(f"if ({fire}) {{")
             self.emit(f"QLS_TR({11 + 2 * s});", ind)
+            self.emit(f"tid = QLS_FRESH_TID({1 + s % 20});  // recompute the addresses below instead of keeping sixteen of them across the ops", ind)
+            # leave
+            if s == ns - 1:
+                later = "false"
+            elif any(always[s + 1:]):
+                later = "true"
+            else:
+                later = " || ".join(sorted({f for f in fires[s + 1:] if f}))
+                later = " || ".join(sorted(set(later.split(" || "))))
+            if later != "false":
+                if later != "true":
+                    self.emit(f"if ({later}) {{", ind)
+                    ind += 1
+                self.emit("if (landed) QLS_BODY_BAR();  // the landing image has been read by everyone", ind)
+                self._exchange(s, True, ind)
+                self.emit("QLS_BODY_BAR();", ind)
+                if later != "true":
+                    ind -= 1
+                    self.emit("} else {", ind)
+            if later != "true":
+                i2 = ind + (1 if later != "false" else 0)
+                self.emit("if (!landed) QLS_BODY_BAR();  // the exchange image has been read by everyone", i2)
+                self._landing(s, True, i2)
+                if later != "false":
+                    self.emit("}", ind)
             if fire:
                 self.emit("}")
-        # write back in the landing layout
-        self.emit("// ---- back to the landing image (the producer warp stores it)")
-        self.emit("if (!landed) QLS_BAR();")
-        last_always = max([j for j in range(ns) if always[j]], default=-1)
-        cands = list(range(max(last_always, 0), ns))
-        for n, j in enumerate(cands):
-            if len(cands) > 1:
-                self.emit(("if" if n == 0 else "else if") + f" (cur == {j}) {{" if n < len(cands) - 1 else "else {")
-                self._landing(j, True, 2)
-                self.emit("}")
-            else:
-                self._landing(j, True, 1)
 
         out: List[str] = []
         out.append(f"// generated by qls_b200/jit.py (version {GEN_VERSION}); do not edit")
@@ -568,22 +620,81 @@ class _Gen:
             out += pred_lines
             out.append("  return !(" + " || ".join(self.preds.values()) + ");")
         out.append("}")
-        out.append("QLS_DEV void qls_tile_body(V* __restrict__ sm, const u64 gbase, const u32 tid, const u32 qls_group,")
+        out.append("QLS_DEV void qls_tile_body(V* __restrict__ sm, const u64 gbase, const u32 tid_in, const u32 qls_group,")
         out.append("                           const unsigned char* __restrict__ pool, u64* qls_trace, const u32 qls_q,")
         out.append("                           volatile u32* qls_cursor) {")
         out.append("  (void)qls_group; (void)pool; (void)qls_trace; (void)qls_q; (void)qls_cursor;")
+        out.append("  // opaque copy of the thread index: keeps the per-stage addresses from being hoisted out of the tile loop")
+        out.append("  // (a dozen values per thread that would live -- spilled -- across the whole pass)")
+        out.append("  u32 tid = QLS_FRESH_TID(0);")
         out.append("  V " + ", ".join(f"a{r}" for r in range(2**KR)) + ";")
-        out.append("  int cur = -1;")
-        out.append("  bool landed = false;")
+        out.append("  bool loaded = false;  // a stage has fired on this tile: the amplitudes are in registers / the exchange image")
+        out.append("  bool landed = false;  // the registers were filled from the landing image (no exchange since)")
         out += pred_lines
-        out += body
-        out.append("}")
+        if not self.share:
+            out += body
+            out.append("}")
+        else:
+            self._flush_chunk()
+            npred = len(self.preds)
+            out.append("  const u32 fmask = 0u" + "".join(f" | ({name} ? {1 << j}u : 0u)" for j, name in enumerate(self.preds.values())) + ";")
+            out.append("  (void)fmask;")
+            out.append("  // the tile program: word 0 = opcode | predicate << 8 | matrix offset << 16, word 1 = thread-control mask | value << 16")
+            out.append("  // (the shuffles make the step words provably warp-uniform: ptxas then keeps the matrix elements in uniform")
+            out.append("  // registers; the words of step k + 1 are fetched while step k runs)")
+            out.append("  u32 n0 = qls_prog[0], n1 = qls_prog[1];")
+            out.append("  for (u32 pc = 1;; ++pc) {")
+            out.append("    const u32 w0 = QLS_UNIFORM(n0), w1 = QLS_UNIFORM(n1);")
+            out.append("    n0 = qls_prog[2 * pc];")
+            out.append("    n1 = qls_prog[2 * pc + 1];")
+            out.append("    const u32 pi = (w0 >> 8) & 0xffu;")
+            out.append("    if (pi != 255u && !((fmask >> pi) & 1u)) continue;")
+            out.append("    switch (w0 & 0xffu) {")
+            out.append("      case 0: return;")
+            for key, (j, lines) in self.shapes.items():
+                out.append(f"      case {1 + j}: {{  // dense {2**key[0]}x{2**key[0]} ({'real' if key[1] else 'complex'}) on register qubits {list(key[2])}, register controls {key[3]:#x}/{key[4]:#x}")
+                out.append("        const V* const M = qls_cm + (w0 >> 16);")
+                out.append("        if ((tid & (w1 & 0xffffu)) == (w1 >> 16)) {")
+                out += ["          " + ln for ln in lines]
+                out.append("        }")
+                out.append("      } break;")
+            prog: List[int] = []
+            nchunk = 0
+            for st in self.steps:
+                if st[0] == "chunk":
+                    out.append(f"      case {32 + nchunk}: {{")
+                    out += ["      " + ln for ln in st[1]]
+                    out.append("      } break;")
+                    prog += [32 + nchunk | (255 << 8), 0]
+                    nchunk += 1
+                else:
+                    _, shape, moff, pi, tm, tv = st
+                    prog += [(1 + shape) | (pi << 8) | (moff << 16), tm | (tv << 16)]
+            prog += [0 | (255 << 8), 0, 0 | (255 << 8), 0]  # (the fetch runs one step ahead)
+            out.append("      default: break;")
+            out.append("    }")
+            out.append("  }")
+            out.append("}")
+            if len(self.shapes) > 31 or nchunk > 200 or len(self.cm) >= 65536 or npred > 31:
+                raise _TooBig()
+            # the program table must precede the function: insert it after the matrix constants
+            table = [f"QLS_CONST u32 qls_prog[{len(prog)}] = {{"]
+            for j in range(0, len(prog), 8):
+                table.append("  " + " ".join(f"{v:#x}u," for v in prog[j:j + 8]))
+            table.append("};")
+            at = next(i for i, ln in enumerate(out) if ln.startswith("QLS_DEV u64 qls_tile_base"))
+            out[at:at] = table
         out.append('#include "rs2_kernel.cuh"')
         return "\n".join(out) + "\n"
 
 
 def generate_source(jp: JPass, mode: Optional[str] = None) -> str:
-    return _Gen(jp, mode).source()
+    try:
+        return _Gen(jp, mode).source()
+    except _TooBig:  # more shapes / steps than the tile program can name: straight-line form
+        g = _Gen(jp, mode)
+        g.share = False
+        return g.source()
 
 
 def smem_bytes(jp: JPass, mode: Optional[str] = None) -> int:
@@ -614,6 +725,8 @@ def _headers() -> Dict[str, str]:
 
 
 NVRTC_OPTIONS = ["--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"]
+if os.environ.get("QLS_JIT_EXPERIMENT", ""):  # timing experiments (wrong results): -DQLS_EXP_<NAME>
+    NVRTC_OPTIONS += ["-DQLS_EXP_" + x.upper() for x in os.environ["QLS_JIT_EXPERIMENT"].split(",")]
 if os.environ.get("QLS_JIT_TRACE", "0") != "0":  # timeline of CTA 0 (tools/jit_trace.py); never set in production
     NVRTC_OPTIONS.append("-DQLS_TRACE")
 
@@ -644,7 +757,12 @@ def compile_source(source: str, use_cache: bool = True) -> bytes:
     out = C.c_void_p()
     size = C.c_uint64()
     log = C.create_string_buffer(1 << 16)
-    rc = lib.qls_jit_compile(source.encode(), names, texts, len(hdr), opts, len(NVRTC_OPTIONS), C.byref(out), C.byref(size),
+    src_path = os.path.join(CACHE_DIR, key + ".cu")  # kept beside the cubin: profilers map the line table to it
+    if use_cache:
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        with open(src_path, "w") as f:
+            f.write(source)
+    rc = lib.qls_jit_compile(source.encode(), src_path.encode(), names, texts, len(hdr), opts, len(NVRTC_OPTIONS), C.byref(out), C.byref(size),
                              log, len(log))
     if rc != 0:
         raise _abi.QlsError(f"NVRTC failed ({rc}): {lib.qls_last_error().decode()}\n{log.value.decode(errors='replace')[-4000:]}")

@@ -154,3 +154,18 @@ def test_sharded_index_offset():
         b = run_program(low, psi0=psi0[sl].copy(), index_offset=rank << n_local, form="jit")
         assert np.max(np.abs(a - b)) < 1e-13
         assert np.max(np.abs(b - want[sl])) < 1e-12
+
+
+def test_program_form_with_shared_gate_shapes(monkeypatch):
+    """QLS_JIT_SHAPES=1: the 4x4 gates of a pass become steps of a tile program whose switch cases are the distinct
+    gate shapes (an experiment kept for heavy passes; off by default)."""
+    monkeypatch.setenv("QLS_JIT_SHAPES", "1")
+    monkeypatch.setenv("QLS_JIT_SHARE_MIN", "0")
+    n = 17
+    qc = hhl_shaped_circuit(n)
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    low = lower_circuit(qc, LoweringOptions())
+    srcs = [jit.generate_source(jit.extract_pass(low, i)) for i in range(low.n_passes) if jit.extract_pass(low, i)]
+    assert any("qls_prog[" in s for s in srcs)
+    got = run_program(low, form="jit")
+    assert np.max(np.abs(got - want)) < 1e-12
