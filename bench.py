@@ -6,8 +6,10 @@
 One *step* = one full solve of the synthetic HHL-shaped circuit (BASELINE.json configs[3] at
 N = 1: QPE + uniformly-controlled RY + inverse QPE, 33 qubits fp64 = 128 GiB state; configs[4] =
 the same circuit at 33 + log2(N) qubits sharded over N GPUs): state preparation, every fused tile
-pass, the reductions P(flag=1) and |x|^2.  metric = amplitude updates per second (sum over fused
-blocks of 2^(n-c)) for the whole job.
+pass, the reductions P(flag=1) and |x|^2.  The headline is ms per solve (``ms_per_step``); ``value`` restates it as
+amplitude updates per second with the job defined on the SOURCE circuit -- the sum over its leaf gates of 2^(n-c),
+c = number of control qubits of the gate -- so that it does not depend on how the lowering
+fuses gates, and is the same job for the CPU arm.
 
 Prints ONE JSON line (see the task contract): value (device-timed, inputs resident in HBM), e2e
 (host buffers in and out through ShapedSolver.solve), roofline (tile-pass kernel vs measured HBM
@@ -50,6 +52,18 @@ def _peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def source_amp_updates(qc) -> tuple:
+    """(sum over the leaf gates of the source circuit of 2^(n - controls), number of leaf gates)."""
+    from qls_b200.circuit import flatten
+
+    leaves, _ = flatten(qc)
+    n = qc.num_qubits
+    total = 0
+    for lf in leaves:
+        total += 2 ** len(lf.targets) if lf.kind == "init" else 2 ** (n - len(lf.controls))
+    return total, len(leaves)
 
 
 class ClockSampler:
@@ -110,19 +124,29 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 
 
+def _use_all_host_threads() -> int:
+    """The BLAS behind NumPy reads its thread count when it is loaded: set it BEFORE the first ``import numpy``
+    (``torch.distributed.run`` exports OMP_NUM_THREADS=1 to its workers)."""
+    cores = os.cpu_count() or 1
+    if "numpy" not in sys.modules:
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(cores)
+    return cores
+
+
 def cpu_reference_sample(n_cpu: int, repeats: int = 1):
     """Time the unfused leaf stream of the HHL-shaped circuit at ``n_cpu`` qubits through
-    ``oracle.numpy_sv`` (reshape/transpose/np.dot per gate).  Returns (amp_updates, seconds)."""
+    ``oracle.numpy_sv`` (reshape/transpose/np.dot per gate).  Returns (source-gate amp updates, seconds, leaves)."""
+    _use_all_host_threads()
     from oracle import numpy_sv
     from oracle.stream import leaves_to_stream
     from qls_b200.circuit import flatten
-    from qls_b200.lower import LoweringOptions, lower_circuit
     from qls_b200.synthetic import hhl_shaped_circuit
 
     qc = hhl_shaped_circuit(n_cpu)
     leaves, phase = flatten(qc)
     stream = leaves_to_stream(leaves, phase)
-    job = lower_circuit(qc, LoweringOptions(dtype="fp64")).amp_updates()  # same job definition as the GPU arm
+    job, _ = source_amp_updates(qc)  # same job definition as the GPU arm
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -148,13 +172,19 @@ def run_reference(args):
     sec = sum(times) / len(times)
     value = job / sec
     cores = os.cpu_count() or 1
+    n_gpu = args.qubits or 33
     sample = (f"HHL-shaped circuit at n={n_cpu} qubits fp64 ({leaves} unfused leaf gates, one reshape/transpose/np.dot "
-              f"pass each = qiskit Statevector._evolve_operator restated in oracle/numpy_sv.py); BLAS threads default")
+              f"pass each = qiskit Statevector._evolve_operator restated in oracle/numpy_sv.py); BLAS threads = "
+              f"{os.environ.get('OMP_NUM_THREADS')}; same_config: false (the GPU arm runs n={n_gpu}: the per-amplitude cost of "
+              f"this algorithm does not depend on n, a solve at n={n_gpu} would take about {sec * 2.0 ** (n_gpu - n_cpu):.0f} s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"hhl_shaped_n{n_cpu}_cpu_sample_of_n{args.qubits or 33}", "n_qubits": n_cpu},
+        "config": {"workload": f"hhl_shaped_n{n_cpu}_cpu_sample_of_n{n_gpu}", "n_qubits": n_cpu, "same_config": False,
+                   "job": "source gates: sum over leaf gates of 2^(n - controls)", "source_gates": leaves,
+                   "amp_updates_per_step": job, "ms_per_solve": sec * 1e3,
+                   "ms_per_solve_extrapolated_to_gpu_arm_size": sec * 1e3 * 2.0 ** (n_gpu - n_cpu)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -164,6 +194,77 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+
+
+def sharded_parity_check(world: int, rank: int, local_rank: int, precision: str, n_local: int = 26) -> dict:
+    """Before anything is timed: the same generator at ``n_local + log2(world)`` qubits, sharded over all ranks and
+    unsharded on rank 0, same right-hand side -- solution slice, P(flag = 1) and |x|^2 must agree to 1e-12 (fp64).
+    Every rank raises if they do not."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from qls_b200.shard import ShardedShapedSolver
+    from qls_b200.solver_shaped import ShapedSolver
+    from qls_b200.synthetic import hhl_shaped_circuit
+
+    n = n_local + int(np.log2(world))
+    qc = hhl_shaped_circuit(n)
+    nb = qc.qregs[0].size
+    b = np.random.default_rng(7).standard_normal(2**nb) + 0j
+    b /= np.linalg.norm(b)
+    sharded = ShardedShapedSolver(qc, nb, precision=precision, device=local_rank)
+    xs, ps, ns = sharded.solve(b)
+    transport = "peer memory" if getattr(sharded.engine, "peers", None) else "nccl"
+    out = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")
+    if rank == 0:
+        single = ShapedSolver(qc, nb, precision=precision, device=local_rank)
+        x1, p1, n1 = single.solve(b)
+        out[0] = float(np.max(np.abs(xs - x1)))
+        out[1] = abs(ps - p1)
+        out[2] = abs(ns - n1)
+        out[3] = float(np.max(np.abs(x1)))
+        del single
+    del sharded
+    torch.cuda.empty_cache()
+    dist.broadcast(out, 0)
+    dx, dp, dn, xmax = (float(v) for v in out.tolist())
+    tol = 1e-12 if precision == "fp64" else 1e-5
+    res = {"n_qubits": n, "ranks": world, "shard_parity_max_abs": max(dx, dp, dn), "x_slice_max_abs": dx, "p_flag1_abs": dp,
+           "norm_sq_abs": dn, "x_slice_max_amplitude": xmax, "tolerance": tol, "transport": transport}
+    if not max(dx, dp, dn) <= tol:
+        raise SystemExit(f"sharded / unsharded mismatch: {res}")
+    return res
+
+
+def state_checks(solver, world: int, precision: str) -> dict:
+    """Size-independent properties of the evolved state (unitary circuit on a unit vector): total norm, P(flag=0) +
+    P(flag=1), <Z_flag> = P0 - P1.  Raises (the run fails) outside 1e-11 in fp64."""
+    import torch
+
+    st = solver.state
+    n_local = st.n_local
+    total = st.norm_sq_range(0, 2**n_local)
+    if world > 1:
+        import torch.distributed as dist
+
+        flag_mask = solver._masks()[0]
+        p1, p0 = st.prob_mask(flag_mask, flag_mask), st.prob_mask(flag_mask, 0)
+        t = torch.tensor([total, p0, p1], dtype=torch.float64, device=st.tensor.device)
+        dist.all_reduce(t)
+        total, p0, p1 = (float(v) for v in t.tolist())
+        z = None
+    else:
+        half = 2 ** (n_local - 1)
+        p1, p0 = st.prob_mask(half, half), st.prob_mask(half, 0)
+        z = st.expectation_z(n_local - 1)
+    tol = 1e-11 if precision == "fp64" else 1e-4
+    out = {"state_norm_sq": total, "p_flag0_plus_p_flag1": p0 + p1, "z_flag": z, "p_flag0_minus_p_flag1": p0 - p1, "tolerance": tol}
+    bad = abs(total - 1.0) > tol or abs(p0 + p1 - 1.0) > tol or (z is not None and abs(z - (p0 - p1)) > tol)
+    out["passed"] = not bad
+    if bad:
+        raise SystemExit(f"state checks failed: {out}")
+    return out
 
 
 def pick_qubits(requested: int, free_bytes: int) -> int:
@@ -200,8 +301,11 @@ def run_gpu(args):
     from qls_b200.synthetic import hhl_shaped_circuit
 
     free_bytes, _total = torch.cuda.mem_get_info()
+    shard_parity = None
     if world > 1:
         from qls_b200.shard import ShardedShapedSolver  # sharded states: 33 + log2(N) qubits
+
+        shard_parity = sharded_parity_check(world, rank, local_rank, args.precision)
 
         n = args.qubits or (pick_qubits(0, free_bytes) + int(np.log2(world)))
         qc = hhl_shaped_circuit(n)
@@ -213,7 +317,8 @@ def run_gpu(args):
         nb = qc.qregs[0].size
         solver = ShapedSolver(qc, nb, precision=args.precision, device=local_rank)
     low = solver.lowered
-    amp_updates = solver.amp_updates_global() if world > 1 else low.amp_updates()
+    amp_updates, n_leaves = source_amp_updates(qc)
+    fused_block_updates = solver.amp_updates_global() if world > 1 else low.amp_updates()
     S = low.amp_bytes()
 
     rng = np.random.default_rng(99)
@@ -253,6 +358,7 @@ def run_gpu(args):
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1) / args.steps
+    checks = state_checks(solver, world, args.precision)  # on the state the last timed solve left in HBM
 
     # ---- timed: tile-pass kernels alone (roofline numerator), CUDA events on the launch stream --
     kern_ms, kern_launches, kern_bytes = solver.time_passes(args.steps)
@@ -296,7 +402,9 @@ def run_gpu(args):
             achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
             traffic, traffic_src = _traffic(kern_bytes / max(1, kern_launches))
             fma = low.fp64_fma_count() if world == 1 else 0.0
-            roofline = {"bound": "hbm", "kernel": "qls_rs_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            jit_n = getattr(solver.program, "jit_passes", 0)
+            roofline = {"bound": "hbm", "kernel": "qls_rs2_pass (specialised per pass, NVRTC)" if jit_n else "qls_rs_pass_kernel",
+                        "specialised_passes": jit_n, "landing": getattr(solver.program, "jit_modes", None), "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                         "launches_per_step": kern_launches, "algorithmic_bytes_per_step": kern_bytes,
                         "algorithmic_bytes_per_launch": kern_bytes / max(1, kern_launches),
@@ -332,12 +440,14 @@ def run_gpu(args):
                                  "not overlapped with compute"}
         line = {
             "metric": METRIC, "value": amp_updates / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": dev_ms, "ms_per_solve": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "config": {"workload": f"hhl_shaped_n{n}" + (f"_sharded_{world}gpu" if world > 1 else ""),
                        "n_qubits": n, "nb": nb, "nl": n - 1 - nb, "state_bytes_per_gpu": S << low.n_local,
                        "fused_passes": st["fused_passes"], "fused_blocks": st["fused_blocks"],
-                       "source_gates": st["source_gates"], "amp_updates_per_step": amp_updates,
+                       "source_gates": n_leaves, "amp_updates_per_step": amp_updates,
+                       "job": "source gates: sum over the leaf gates of the circuit of 2^(n - controls)",
+                       "fused_block_amp_updates_per_step": fused_block_updates,
                        "hbm_bytes_per_step_per_gpu": st["pass_bytes_per_gpu"] + (S << low.n_local),
                        "l2_policy": "inputs_larger_than_L2" if (S << low.n_local) > (256 << 20) else "state_fits_L2_no_flush",
                        "program": "lowered once outside the timed region; b differs per solve only through init"},
@@ -348,7 +458,9 @@ def run_gpu(args):
             "remap": remap,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
-            "result_check": {"p_flag1": last[0], "norm_sq": last[1], "e2e_p_flag1": p_flag},
+            "result_check": dict({"p_flag1": last[0], "norm_sq": last[1], "e2e_p_flag1": p_flag,
+                                  "e2e_matches_device_run": abs(last[0] - p_flag) <= 1e-12 and abs(last[1] - norm_sq) <= 1e-12},
+                                 **checks, **({"sharded_vs_unsharded": shard_parity} if shard_parity else {})),
         }
         if args.all_configs and world == 1:
             # BASELINE.json configs[1] and configs[2] on the same box (secondary lines; not the headline)
@@ -375,7 +487,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--qubits", type=int, default=0, help="total qubits (default: 33 on 1 GPU if it fits)")
-    ap.add_argument("--cpu-qubits", type=int, default=23, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-qubits", type=int, default=22, help="size of the bounded CPU sample")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--profile-passes", action="store_true", help="print per-pass timings to stderr")
     ap.add_argument("--no-all-configs", dest="all_configs", action="store_false",

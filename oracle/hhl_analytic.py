@@ -71,40 +71,72 @@ def _bitrev(x: int, nbits: int) -> int:
     return int(format(x, f"0{nbits}b")[::-1], 2) if nbits else 0
 
 
+def _bitrev_perm(nbits: int) -> np.ndarray:
+    idx = np.arange(2**nbits)
+    rev = np.zeros_like(idx)
+    for j in range(nbits):
+        rev |= ((idx >> j) & 1) << (nbits - 1 - j)
+    return rev
+
+
+def _wht(a: np.ndarray) -> np.ndarray:
+    """Unnormalised Walsh-Hadamard transform along axis 0 (natural order: H^{(x)m}[x][y] = (-1)^{popcount(x & y)})."""
+    a = a.copy()
+    n = a.shape[0]
+    h = 1
+    while h < n:
+        v = a.reshape(n // (2 * h), 2, h, -1)
+        lo, hi = v[:, 0].copy(), v[:, 1].copy()
+        v[:, 0] = lo + hi
+        v[:, 1] = lo - hi
+        h *= 2
+    return a
+
+
+def eigenphase_table(w_eig: np.ndarray, t: float, dim_c: int) -> np.ndarray:
+    """``exp(2*pi*i*phi_k*x)`` for every clock value ``x`` and eigenvalue ``k`` (``phi_k = lambda_k t / 2 pi``).
+    ``phi_k * x`` reaches ``2**(nl-1)`` turns, which costs ``nl - 1`` bits of a double: the turn count is
+    reduced modulo 1 in extended precision, so that the table is good to ~1e-16 at every ``x`` (the circuit
+    the oracle describes applies ``U**(2**j)`` exactly)."""
+    ld = np.longdouble
+    two_pi = 2 * np.arccos(ld(-1))
+    phi = w_eig.astype(ld) * ld(t) / two_pi
+    turns = np.outer(np.arange(dim_c).astype(ld), phi)
+    turns -= np.floor(turns)
+    ang = (two_pi * turns).astype(np.float64)
+    return np.cos(ang) + 1j * np.sin(ang)
+
+
 def hhl_state(matrix: np.ndarray, vector: np.ndarray) -> np.ndarray:
-    """Final ``2**(nb+nl+1)`` amplitude vector of the HHL circuit (register order b, clock, flag)."""
-    matrix = np.asarray(matrix, dtype=complex)
-    nb, nl, delta, t, _ = hhl_parameters(matrix)
+    """Final ``2**(nb+nl+1)`` amplitude vector of the HHL circuit (register order b, clock, flag).
+
+    Per eigenpair ``(lambda_k, u_k)`` the clock/flag register ends in ``(W_k^dagger (x) I) Rot (W_k|0> (x) |0>)`` with
+    ``W_phi = R F^dagger diag(exp(2 pi i phi x)) H^{(x)nl}``; ``F`` is applied as an FFT and ``H^{(x)nl}`` as a
+    Walsh-Hadamard transform, for all ``k`` at once, so that the N = 2**10, nl = 12 case of BASELINE.json configs[1]
+    (2**23 amplitudes) is a few seconds of host time.  The eigen-decomposition is taken of the matrix AS GIVEN
+    (``np.linalg.eigh`` on a real array for a real matrix): eigenvalue bits differ between LAPACK's real and complex
+    drivers at the 1e-16 level, and ``U**(2**(nl-1))`` amplifies that by ``2**(nl-1)``."""
+    a = np.asarray(matrix)
+    nb, nl, delta, t, _ = hhl_parameters(a)
     dim_c = 2**nl
-    w_eig, v_eig = np.linalg.eigh(matrix)
+    w_eig, v_eig = np.linalg.eigh(a)
     b = np.asarray(vector, dtype=complex).reshape(-1)
     b = b / np.linalg.norm(b)
     beta = v_eig.conj().T @ b
-    x = np.arange(dim_c)
-    dft_dag = np.exp(-2j * np.pi * np.outer(x, x) / dim_c) / math.sqrt(dim_c)  # F^dagger
-    rev = np.array([_bitrev(i, nl) for i in range(dim_c)])
-    perm = np.zeros((dim_c, dim_c))
-    perm[rev, x] = 1.0  # R |c> = |rev(c)>
-    theta_by_value = reciprocal_angle_by_value(nl, delta)
-    theta_by_reg = theta_by_value[rev]  # register index r holds value rev(r)
-    psi = np.zeros((2, dim_c, 2**nb), dtype=complex)
-    for k in range(len(w_eig)):
-        phi = w_eig[k] * t / (2 * np.pi)
-        full_w = perm @ dft_dag @ np.diag(np.exp(2j * np.pi * phi * x)) @ _hadamard(nl)
-        w0 = full_w[:, 0]  # W_k |0...0>
-        chi0 = np.cos(theta_by_reg / 2) * w0
-        chi1 = np.sin(theta_by_reg / 2) * w0
-        psi[0] += beta[k] * np.outer(full_w.conj().T @ chi0, v_eig[:, k])
-        psi[1] += beta[k] * np.outer(full_w.conj().T @ chi1, v_eig[:, k])
-    return psi.reshape(-1)
-
-
-def _hadamard(m: int) -> np.ndarray:
-    h = np.array([[1.0]])
-    h1 = np.array([[1, 1], [1, -1]]) / math.sqrt(2)
-    for _ in range(m):
-        h = np.kron(h1, h)
-    return h
+    rev = _bitrev_perm(nl)
+    phase = eigenphase_table(w_eig, t, dim_c)                    # [x, k]
+    w0 = np.empty_like(phase)
+    w0[rev] = np.fft.fft(phase, axis=0) / dim_c                   # W_k|0> = R F^dagger (phase / sqrt(D)), [register, k]
+    theta_by_reg = reciprocal_angle_by_value(nl, delta)[rev]      # register index r holds value rev(r)
+    out = []
+    for rot in (np.cos(theta_by_reg / 2), np.sin(theta_by_reg / 2)):
+        chi = rot[:, None] * w0
+        z = chi[rev]                                              # R^T
+        z = np.fft.ifft(z, axis=0) * math.sqrt(dim_c)             # F
+        z *= phase.conj()
+        z = _wht(z) / math.sqrt(dim_c)                            # H^{(x)nl}
+        out.append(z @ (beta[:, None] * v_eig.T))                 # sum_k beta_k (W_k^dagger chi_k)[c] u_k[b]
+    return np.stack(out).reshape(-1)
 
 
 def hhl_solution(matrix: np.ndarray, vector: np.ndarray) -> np.ndarray:

@@ -71,8 +71,16 @@ class NumPyMatrix:
         return self._eig
 
     def evolved(self, power: int = 1) -> np.ndarray:
+        """``expm(i A t)**power`` from the eigen-decomposition.  The angle ``lambda t power`` reaches thousands of radians
+        for the top clock qubits (``power = 2**(nl-1)``); it is reduced modulo 2 pi in extended precision so that the
+        phases stay good to ~1e-16 (a double would lose ``nl - 1`` bits: 1e-12 at nl = 12)."""
         w, v = self._eigh()
-        return (v * np.exp(1j * w * self.evolution_time * power)) @ v.conj().T
+        ld = np.longdouble
+        two_pi = 2 * np.arccos(ld(-1))
+        turns = w.astype(ld) * ld(self.evolution_time) / two_pi * ld(int(power))
+        turns -= np.floor(turns)
+        ang = (two_pi * turns).astype(np.float64)
+        return (v * (np.cos(ang) + 1j * np.sin(ang))) @ v.conj().T
 
     def power(self, power: int) -> QuantumCircuit:
         nq = self.num_state_qubits

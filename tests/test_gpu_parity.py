@@ -170,21 +170,29 @@ def test_hhl_toy_models_vs_golden(cuda_device, name):
     assert math.isclose(res.euclidean_norm, numpy_sv.hhl_norm(want, n, hhl.scaling), rel_tol=1e-12)
 
 
-def test_hhl_gemm_block_path(cuda_device):
-    """Dense controlled-e^{iAt} blocks on a 6-qubit data register go through qls_ctrl_gemm."""
+@pytest.mark.parametrize("nb", [6, 10])
+def test_hhl_gemm_block_path(cuda_device, nb):
+    """Dense controlled-e^{iAt} blocks on the data register go through qls_ctrl_gemm.  nb = 10 is BASELINE.json
+    configs[1] at its real size (tridiagonal N = 2**10, reference formula nl = 12, n = 23: 24 complex 1024x1024
+    products on 2**22 rows each) against the closed-form state, at the north-star tolerance."""
     from qls_b200.hhl import HHL
     from qls_b200.lower import lower_circuit
     from qls_b200.statevector import Statevector
     from qls_b200.toymodels import TridiagonalToeplitz
 
-    model = TridiagonalToeplitz(6)
+    model = TridiagonalToeplitz(nb)
     hhl = HHL(power_mode="eig")
     qc = hhl.construct_circuit(model.matrix_a, model.vector_b)
-    assert any(s.kind == "gemm" for s in lower_circuit(qc).steps)
-    got = Statevector(qc).data
+    if nb == 10:
+        assert (qc.num_qubits, hhl.nl) == (23, 12)
+    assert sum(s.kind == "gemm" for s in lower_circuit(qc).steps) == 2 * hhl.nl
+    sv = Statevector(qc)
+    got = sv.data
     want = hhl_analytic.hhl_state(model.matrix_a, model.vector_b)
-    assert np.max(np.abs(got - want)) <= 5e-12  # 2*nl dense 64x64 products: a few more roundings
+    assert np.max(np.abs(got - want)) <= TOL64
     assert _fidelity(got, want) >= FID
+    half = 2 ** (qc.num_qubits - 1)
+    assert abs(sv.norm_sq_range(half, 2**nb) - float(np.sum(np.abs(want[half:half + 2**nb]) ** 2))) <= 1e-13
 
 
 def test_reductions(cuda_device):
@@ -306,6 +314,32 @@ def test_estimator_wide_operator_matvec(cuda_device):
         for k in range(5):
             psi = numpy_sv.run(nq + 1, circuit_to_stream(circ.assign_parameters(thetas[k])))
             assert abs(got[k] - numpy_sv.expectation_z(psi, 0)) <= 1e-12
+
+
+def test_estimator_full_batch_of_4096(cuda_device):
+    """BASELINE.json configs[2] at its real size: ONE launch of 4096 Hadamard-test circuits at 10 qubits (ansatz on 9
+    data qubits, controlled dense 9-qubit unitary), real and imaginary part; 32 circuits sampled across the batch are
+    checked against bind + oracle + <Z_0>."""
+    from qls_b200.circuit import QuantumCircuit
+    from qls_b200.estimator import B200Estimator
+    from qls_b200.library import RealAmplitudes
+    from qls_b200.vqls import HadamardTest
+
+    rng = np.random.default_rng(7)
+    nq, k = 9, 4096
+    ansatz = RealAmplitudes(nq, reps=3)
+    op = QuantumCircuit(nq)
+    op.unitary(random_unitary(nq, rng), list(range(nq)))
+    test = HadamardTest([op], apply_initial_state=ansatz)
+    thetas = np.random.default_rng(4321).uniform(-np.pi, np.pi, (k, ansatz.num_parameters))
+    est = B200Estimator()
+    picks = sorted(set(int(x) for x in np.random.default_rng(1).integers(0, k, 30)) | {0, k - 1})
+    for circ in test.circuits:
+        got = est.run([circ] * k, ["I" * nq + "Z"] * k, list(thetas)).result().values
+        assert got.shape == (k,) and np.all(np.abs(got) <= 1 + 1e-12)
+        for j in picks:
+            psi = numpy_sv.run(nq + 1, circuit_to_stream(circ.assign_parameters(thetas[j])))
+            assert abs(got[j] - numpy_sv.expectation_z(psi, 0)) <= 1e-12
 
 
 def test_vqls_2x2_through_the_facade(cuda_device, tmp_path, monkeypatch):
