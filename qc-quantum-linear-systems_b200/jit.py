@@ -35,7 +35,7 @@ KERNEL_NAME = "qls_rs2_pass"
 T = 12  # tile bits of the specialised kernels (complex128)
 KR = 4  # register qubits per thread
 THREADS = 2 * 256 + 128  # two consumer groups + the producer warpgroup
-GEN_VERSION = 21  # bump when the generated code or the runtime headers change meaning
+GEN_VERSION = 22  # bump when the generated code or the runtime headers change meaning
 
 
 # --------------------------------------------------------------------------------------
@@ -504,6 +504,23 @@ class _Gen:
         ind -= 1
         self.emit("}", ind)
 
+    def tile_order(self) -> List[Tuple[int, int]]:
+        """(bit of the tile ordinal, state-index position) pairs of ``qls_tile_base``.
+
+        Default: the free index positions in ascending order.  QLS_JIT_TILE_ORDER=pattern gives the control qubits OUTSIDE
+        the tile the top bits of the ordinal, so that a CTA works through all tiles of one control pattern (= one subset of
+        the pass's code) before the next pattern starts.  Measured at n = 33 (profiles/r02_tile_order_ab_n33.txt): no
+        difference (935 vs 940 ms per solve) -- the control qubits are high clock qubits, so the pattern of a CTA's
+        consecutive tiles already changes only every ~50 tiles in index order."""
+        pos = [dst + w for _, wd, dst in sorted(self.jp.fseg) for w in range(wd)]
+        if os.environ.get("QLS_JIT_TILE_ORDER", "index") == "pattern":
+            ctl = 0
+            for st in self.jp.stages:
+                for op in st.ops:
+                    ctl |= op.xc_mask
+            pos = [p for p in pos if not (ctl >> p) & 1] + [p for p in pos if (ctl >> p) & 1]
+        return list(enumerate(pos))
+
     # -- whole unit ------------------------------------------------------------------------
     def source(self) -> str:
         jp = self.jp
@@ -605,8 +622,7 @@ class _Gen:
             out.append("  " + " ".join(f"{{{_hexf(v.real)}, {_hexf(v.imag)}}}," for v in cm[j:j + 2]))
         out.append("};")
         out.append("QLS_DEV u64 qls_tile_base(const u64 t) {")
-        out.append(f"  return {deposit_expr('t', [(src + w, dst + w) for src, wd, dst in jp.fseg for w in range(wd)], wide=True)}"
-                   f" | {jp.fix_val:#x}ull;")
+        out.append(f"  return {deposit_expr('t', self.tile_order(), wide=True)} | {jp.fix_val:#x}ull;")
         out.append("}")
         out.append("QLS_DEV u64 qls_run_offset(const u32 r) {")
         out.append(f"  return {deposit_expr('(u64)r', [(j, q) for j, q in enumerate(jp.high)], wide=True)};")

@@ -584,6 +584,8 @@ class _Emitter:
                 self.steps.append(Step("init", qubits=b.targets, amps=b.amps))
                 self.zero = set(range(self.n)) - set(b.targets) - set(self.opts.awake_after_init)
             else:
+                if tuple(b.targets) != tuple(range(len(b.targets))):
+                    raise ValueError(f"a GEMM block acts on positions 0..nb-1 (csrc/ctrl_gemm.cu), got targets {tuple(b.targets)}")
                 if self.zero is not None:
                     self.zero -= set(b.targets)
                 mask = sum(1 << q for q in b.controls)

@@ -112,6 +112,13 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
     # keeps qubits that stay |0> for long (the HHL flag) LOCAL, where every rank profits from skipping their |1> half.
     # Remaining global positions: the qubits touched last.
     pinned = set(blocks[0].targets) if blocks and blocks[0].kind == "init" else set()
+    # a GEMM block (dense controlled e^{iAt} on the data register) always executes on positions 0..nb-1
+    # (csrc/ctrl_gemm.cu): its target qubits never leave their low positions, whatever ``protect_low`` says
+    gemm_pinned: set = set()
+    for b in blocks:
+        if b.kind == "gemm":
+            gemm_pinned |= set(b.targets)
+    pinned |= gemm_pinned
     foldable: Dict[int, int] = {}
     if blocks and blocks[0].kind == "init" and fold_first_gates:
         seen: set = set()
@@ -173,7 +180,7 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
             incoming = sorted((q for q in range(n) if phys[q] >= n_local), key=lambda q: next_touch(q, i))
             incoming = [q for q in incoming if q in need_global or next_touch(q, i) < inf]
             # evict: local qubits with the farthest next touch, high positions first, never the low run
-            cands = [q for q in range(n) if protect_low <= phys[q] < n_local and q not in b.touched]
+            cands = [q for q in range(n) if protect_low <= phys[q] < n_local and q not in b.touched and q not in gemm_pinned]
             cands.sort(key=lambda q: (-next_touch(q, i), -phys[q]))
             pairs = []
             for qin in incoming:
@@ -405,19 +412,26 @@ class ShardedShapedSolver:
         chunk_amps = 1 << int(os.environ.get("QLS_REMAP_CHUNK_LOG2", int(chunk_amps).bit_length() - 1))
         self.engine = CudaShardEngine(self.plan, self.rank, precision, device, chunk_amps)
         self.runner = ShardedRunner(self.plan, self.engine, self.rank, self.world, chunk_amps, dist)
+        self.transport_fallback: Optional[str] = None  # why the peer-memory remaps are not in use (None: they are, or were not asked for)
         if os.environ.get("QLS_REMAP_P2P", "1") == "1":
             # remaps through peer memory (CUDA IPC + NVLink loads/stores: 590 GB/s per direction measured) instead of
             # pack + NCCL send/recv + unpack (446 GB/s); all ranks must agree, so a failure anywhere falls back everywhere
+            why = ""
             try:
                 self.engine.map_peers(dist)
-                ok = 1
-            except Exception:  # noqa: BLE001 -- no IPC / no peer access on this box
+            except Exception as exc:  # noqa: BLE001 -- no IPC / no peer access on this box
                 self.engine.peers = None
-                ok = 0
-            flags: List[Any] = [None] * self.world
-            dist.all_gather_object(flags, ok)
-            if not all(flags):
+                why = f"rank {self.rank}: {type(exc).__name__}: {exc}"
+            reasons: List[Any] = [None] * self.world
+            dist.all_gather_object(reasons, why)
+            if any(reasons):
+                # never silent: the fall-back costs bandwidth (pack + NCCL send/recv + unpack, 446 vs 590 GB/s)
                 self.engine.peers = None
+                self.transport_fallback = "; ".join(r for r in reasons if r)
+                if self.rank == 0:
+                    import sys
+
+                    sys.stderr.write(f"qls_b200.shard: peer-memory remaps unavailable, using the NCCL path ({self.transport_fallback})\n")
         self.state = self.engine.state
         first = self.plan.segments[0].lowered
         if not (first.steps and first.steps[0].kind == "init"):

@@ -28,10 +28,15 @@ class Statevector:
             self._state, self.num_qubits, self.program = data._state, data.num_qubits, data.program
             return
         if isinstance(data, QuantumCircuit):
+            # HHL.solve leaves the evolved state on the circuit it returns (the reference simulates that circuit a second
+            # time, hhl_qiskit_implementation.py:49).  The entry is only valid for the circuit as it was (same number of
+            # instructions), the same precision and the same device.
             cached = getattr(data, "_sv_cache", None)
-            if cached is not None and cached.precision == precision and options is None and fused:
-                self._state, self.num_qubits, self.program = cached._state, cached.num_qubits, cached.program
-                return
+            if cached is not None and options is None and fused:
+                key, sv = cached
+                if key == (len(data.data), precision, device if device is not None else sv._state.device):
+                    self._state, self.num_qubits, self.program = sv._state, sv.num_qubits, sv.program
+                    return
             opts = dataclasses.replace(options) if options is not None else LoweringOptions(dtype=precision)
             opts.dtype = precision
             opts.zero_start = True  # the program below runs on |0...0>: qubits are known to be |0> until first acted on

@@ -227,3 +227,21 @@ def test_multi_process_gloo_exchange(tmp_path, seed, world):
     assert list(np.load(tmp_path / "layout.npy")) == plan.final_layout
     got = _logical_state(plan, shards)
     assert np.max(np.abs(got - want)) < 1e-12
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gemm_register_is_pinned(world):
+    """A GEMM block always executes on positions 0..nb-1 (csrc/ctrl_gemm.cu): the planner must never evict one of its
+    target qubits, also when the register is wider than ``protect_low`` (nb = 9 > 8).  Without the pin, data qubit 8 is
+    evicted during the inverse QFT and half of the GEMM blocks would act on the wrong qubits (the lowering now refuses
+    such a block instead of emitting it)."""
+    from qls_b200.hhl import HHL
+    from qls_b200.toymodels import TridiagonalToeplitz
+
+    model = TridiagonalToeplitz(9)
+    hhl = HHL(power_mode="eig")
+    qc = hhl.construct_circuit(model.matrix_a, model.vector_b)
+    plan = plan_sharded(qc, world, LoweringOptions(dtype="fp64"))
+    gemms = [s for seg in plan.segments if seg.kind == "local" for s in seg.lowered.steps if s.kind == "gemm"]
+    assert len(gemms) == 2 * hhl.nl and all(s.nb == 9 for s in gemms)
+    assert all(plan.final_layout[q] == q for q in range(9))
