@@ -129,7 +129,7 @@ class HHL:
         nb = qc.qregs[0].size
         half = 2 ** (qc.num_qubits - 1)
         norm2 = sv.norm_sq_range(half, 2**nb)
-        qc._sv_cache = ((len(qc.data), self.precision, sv._state.device), sv)  # type: ignore[attr-defined]
+        qc._sv_cache = ((len(qc.data), self.precision, getattr(sv, "device", self.device)), sv)  # type: ignore[attr-defined]
         return float(np.real(math.sqrt(norm2) / self.scaling))
 
     def solve(self, matrix: Union[np.ndarray, Sequence], vector: Union[np.ndarray, Sequence, QuantumCircuit],

@@ -34,7 +34,7 @@ class Statevector:
             cached = getattr(data, "_sv_cache", None)
             if cached is not None and options is None and fused:
                 key, sv = cached
-                if key == (len(data.data), precision, device if device is not None else sv._state.device):
+                if key == (len(data.data), precision, device if device is not None else key[2]):
                     self._state, self.num_qubits, self.program = sv._state, sv.num_qubits, sv.program
                     return
             opts = dataclasses.replace(options) if options is not None else LoweringOptions(dtype=precision)
@@ -56,6 +56,10 @@ class Statevector:
         self._state.write(0, arr)
 
     # -- qiskit-shaped accessors ----------------------------------------------------------
+    @property
+    def device(self) -> int:
+        return self._state.device
+
     @property
     def dim(self) -> int:
         return 2**self.num_qubits
