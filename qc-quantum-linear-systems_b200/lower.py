@@ -889,7 +889,7 @@ class _Emitter:
     def _rs_table_fields(self, op: _abi.QlsRsOp, qubits: Sequence[int], local_pos, rho, tbit) -> bool:
         """Index fields of a table whose bit j is ``qubits[j]``: thread bits -> tseg, register
         qubits -> rt[], everything else -> xseg on the global base index."""
-        if len(qubits) > 16:
+        if len(qubits) > 30:
             return False
         tpairs, xpairs, rbits = [], [], []
         for j, q in enumerate(qubits):
@@ -903,6 +903,8 @@ class _Emitter:
         tpairs.sort()
         ts, xs = _segments(tpairs), _segments(xpairs)
         if len(ts) > _abi.QLS_MAX_SEG or len(xs) > _abi.QLS_MAX_SEG:
+            return False
+        if any(j >= 16 for _, j in rbits):  # rt[] holds 16-bit words: register qubits must index the low table bits
             return False
         op.n_tseg, op.n_xseg = len(ts), len(xs)
         for j, (src, w, dst) in enumerate(ts):
@@ -938,7 +940,10 @@ class _Emitter:
             op = _abi.QlsRsOp()
             op.kind = _abi.QLS_RS_MUXRY
             op.r[0] = rho[local_pos[b.targets[0]]]
-            sel = sorted(b.selectors)
+            # selectors inside the tile index the low table bits, the ones outside the high bits: a table over more than 16
+            # selectors (17-18 clock qubits on a sharded 34-36 qubit state) keeps its register-qubit fields within rt[]'s
+            # 16-bit words -- without this the whole pass fell back to the shared-memory sweep kernel
+            sel = sorted(b.selectors, key=lambda q: (q not in local_pos, q))
             ang = _mux_expand(b.angles, b.selectors, sel) if list(sel) != list(b.selectors) else b.angles
             if not self._rs_table_fields(op, sel, local_pos, rho, tbit):
                 raise _RsUnsupported("multiplexer table fields")

@@ -55,6 +55,9 @@ class ShardedPlan:
     final_layout: List[int]
     amp_updates: int  # whole-state sum over fused blocks of 2^(n-c)
     n_source_gates: int
+    # logical qubit -> 2x2 matrix of its LAST gate, not applied to the state (``defer_final_1q``): the qubit is on a global
+    # position at the end of the plan and a consumer that only projects it (the solver path) folds the gate into its reduction
+    deferred: Dict[int, np.ndarray] = field(default_factory=dict)
 
     @property
     def n_swaps(self) -> int:
@@ -74,7 +77,13 @@ def _relabel(b: Block, phys: Sequence[int]) -> Block:
 
 
 def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[LoweringOptions] = None,
-                 protect_low: int = 8, fold_first_gates: bool = True) -> ShardedPlan:
+                 protect_low: int = 8, fold_first_gates: bool = True, defer_final_1q: bool = False) -> ShardedPlan:
+    """``defer_final_1q``: an uncontrolled one-qubit gate that is the LAST block referring to its qubit at all is not applied
+    if the qubit sits on a global position when the gate is reached; it is returned in ``ShardedPlan.deferred`` instead.
+    For a consumer that only needs the state projected on one value of that qubit (the HHL solver path reads the
+    clock = 0 slice; the final gates of inverse QPE are the Hadamards of the clock qubits) the gate becomes a weighted sum
+    over ranks, <0|G = G[0][0]<0| + G[0][1]<1| -- an all-reduce of the 2^nb-amplitude slice instead of an exchange of up to
+    7/8 of every shard.  ``Statevector``-style consumers keep the full plan (default)."""
     g = int(round(math.log2(world_size)))
     if 2**g != world_size:
         raise ValueError("world size must be a power of two")
@@ -92,10 +101,20 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
             blocks[0] = Block("init", b0.targets, amps=b0.amps * ph[0])
         else:
             blocks.insert(0, Block("diag", (), factors=[((), ph)], n_source=0))
+    # candidates for deferral: uncontrolled 1-qubit gates after which nothing refers to their qubit any more
+    last_ref = [-1] * n
+    for i, b in enumerate(blocks):
+        for q in b.support:
+            last_ref[q] = i
+    defer_ids = {id(b) for i, b in enumerate(blocks)
+                 if defer_final_1q and b.kind == "dense" and len(b.targets) == 1 and not b.controls and last_ref[b.targets[0]] == i}
     # next-touch table (Belady): for every block index, the next index at which each logical qubit is touched
+    # (a deferrable gate does not count: it never needs its qubit to be local)
     inf = len(blocks) + 1
     touch_at: List[List[int]] = [[] for _ in range(n)]
     for i, b in enumerate(blocks):
+        if id(b) in defer_ids:
+            continue
         for q in b.touched:
             touch_at[q].append(i)
 
@@ -149,9 +168,12 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
         blocks = [b for i, b in enumerate(blocks) if i not in drop]
         touch_at = [[] for _ in range(n)]
         for i, b in enumerate(blocks):
+            if id(b) in defer_ids:
+                continue
             for q in b.touched:
                 touch_at[q].append(i)
     initial = list(phys)
+    deferred: Dict[int, np.ndarray] = {}
 
     segments: List[Segment] = []
     cur: List[Block] = []
@@ -170,6 +192,9 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
             cur = []
 
     for i, b in enumerate(blocks):
+        if id(b) in defer_ids and phys[b.targets[0]] >= n_local:
+            deferred[b.targets[0]] = np.asarray(b.matrix, dtype=complex).reshape(2, 2)
+            continue
         if b.kind != "init":
             amp_updates += 2 ** (n - len(b.controls))
         need_global = [q for q in b.touched if phys[q] >= n_local]
@@ -198,7 +223,27 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
             del where
         cur.append(_relabel(b, phys))
     close_local()
-    return ShardedPlan(n, n_local, g, segments, initial, list(phys), amp_updates, len(leaves))
+    return ShardedPlan(n, n_local, g, segments, initial, list(phys), amp_updates, len(leaves), deferred)
+
+
+def solution_slice_plan(plan: ShardedPlan, nb: int, rank: int) -> Tuple[np.ndarray, np.ndarray, complex]:
+    """Which entries of the solution slice (last qubit = 1, qubits nb..n-2 = 0, qubits 0..nb-1 = i) ``rank`` contributes to,
+    their addresses in its shard, and the rank's weight (product of G[0][own bit] over the deferred gates G)."""
+    fl, nl, n = plan.final_layout, plan.n_local, plan.num_qubits
+    i = np.arange(2**nb, dtype=np.int64)
+    idx = np.zeros(2**nb, dtype=np.int64)
+    for q in range(nb):
+        idx |= ((i >> q) & 1) << fl[q]
+    idx |= 1 << fl[n - 1]
+    weight = 1.0 + 0.0j
+    dmask = 0
+    for q, m in plan.deferred.items():
+        g = fl[q] - nl
+        dmask |= 1 << g
+        weight *= complex(m[0, (rank >> g) & 1])
+    owner = idx >> nl
+    sel = np.nonzero((owner & ~dmask) == (rank & ~dmask))[0]
+    return sel, idx[sel] & (2**nl - 1), weight
 
 
 # --------------------------------------------------------------------------------------
@@ -408,7 +453,9 @@ class ShardedShapedSolver:
         opts = options or LoweringOptions(dtype=precision)
         opts.dtype = precision
         self.n, self.nb = circuit.num_qubits, int(nb)
-        self.plan = plan_sharded(circuit, self.world, opts)
+        # the solver path only reads the clock = 0 slice: the final Hadamards of clock qubits that are on global positions at
+        # the end become rank weights of the slice's all-reduce instead of one more exchange (QLS_SHARD_DEFER=0: full plan)
+        self.plan = plan_sharded(circuit, self.world, opts, defer_final_1q=os.environ.get("QLS_SHARD_DEFER", "1") != "0")
         chunk_amps = 1 << int(os.environ.get("QLS_REMAP_CHUNK_LOG2", int(chunk_amps).bit_length() - 1))
         self.engine = CudaShardEngine(self.plan, self.rank, precision, device, chunk_amps)
         self.runner = ShardedRunner(self.plan, self.engine, self.rank, self.world, chunk_amps, dist)
@@ -480,11 +527,42 @@ class ShardedShapedSolver:
             nondata |= 1 << fl[q]
         return flag, flag, nondata, flag
 
+    def _slice_plan(self):
+        """(indices of the solution slice this rank contributes to, their local addresses, this rank's weight).
+
+        The slice is flag = 1, clock = 0, data = i.  A rank contributes the entries whose owner agrees with it on every
+        global position EXCEPT those of deferred qubits; there its own bit b selects the weight G[0][b] of the deferred
+        gate G (<0|G|psi> = G[0][0] psi_0 + G[0][1] psi_1)."""
+        if getattr(self, "_slice_cache", None) is None:
+            import torch
+
+            sel, local, weight = solution_slice_plan(self.plan, self.nb, self.rank)
+            dev = self.state.tensor.device
+            self._slice_cache = (torch.from_numpy(sel).to(dev), torch.from_numpy(local).to(dev), weight)
+        return self._slice_cache
+
+    def _slice(self):
+        """The solution slice (device tensor, complete on every rank after the all-reduce)."""
+        import torch
+
+        sel, local, weight = self._slice_plan()
+        x = torch.zeros(2**self.nb, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
+        if sel.numel():
+            x[sel] = self.state.tensor[local] * weight if weight != 1.0 else self.state.tensor[local]
+        self.dist.all_reduce(torch.view_as_real(x))
+        return x
+
     def reduce(self) -> Tuple[float, float]:
         import torch
 
         m1, v1, m2, v2 = self._masks()
         p_flag = self.state.prob_mask(m1, v1)
+        if self.plan.deferred:
+            # |x|^2 of the state AFTER the deferred gates = norm of the rank-weighted slice
+            x = self._slice()
+            t = torch.tensor([p_flag], dtype=torch.float64, device=self.state.tensor.device)
+            self.dist.all_reduce(t)
+            return float(t.item()), float((x.real.double() ** 2 + x.imag.double() ** 2).sum().item())
         norm_sq = self.state.prob_mask(m2, v2)
         t = torch.tensor([p_flag, norm_sq], dtype=torch.float64, device=self.state.tensor.device)
         self.dist.all_reduce(t)
@@ -492,27 +570,10 @@ class ShardedShapedSolver:
         return float(out[0]), float(out[1])
 
     def solve(self, b_host: np.ndarray):
-        import torch
-
         self._prepare(b_host=np.asarray(b_host).reshape(-1))
         self._run_segments()
         p_flag, norm_sq = self.reduce()
-        # the solution slice: flag = 1, clock = 0, data = i, at the data qubits' final physical positions
-        fl = self.plan.final_layout
-        idx = np.zeros(2**self.nb, dtype=np.int64)
-        i = np.arange(2**self.nb, dtype=np.int64)
-        for q in range(self.nb):
-            idx |= ((i >> q) & 1) << fl[q]
-        idx |= 1 << fl[self.n - 1]
-        owner = idx >> self.plan.n_local
-        local = idx & (2**self.plan.n_local - 1)
-        x = torch.zeros(2**self.nb, dtype=self.state.tensor.dtype, device=self.state.tensor.device)
-        sel = np.nonzero(owner == self.rank)[0]
-        if sel.size:
-            li = torch.from_numpy(local[sel]).to(self.state.tensor.device)
-            x[torch.from_numpy(sel).to(self.state.tensor.device)] = self.state.tensor[li]
-        xr = torch.view_as_real(x)
-        self.dist.all_reduce(xr)
+        x = self._slice()
         return x.cpu().numpy(), p_flag, norm_sq
 
     def stats(self) -> Dict[str, int]:

@@ -141,3 +141,31 @@ def test_large_state_matches_interpreter_kernels(cuda_device):
     rng = np.random.default_rng(5)
     for off in [0, half] + [int(x) for x in rng.integers(0, 2**n - 2**16, 6)]:
         assert np.max(np.abs(a.read(off, 2**16) - b.read(off, 2**16))) <= TOL64
+
+
+@pytest.mark.parametrize("jit_on", [True, False])
+def test_multiplexer_over_seventeen_selectors(cuda_device, jit_on):
+    """More than 16 selector qubits (ExactReciprocal of a sharded 34-36 qubit solve): register-stage form on both the
+    specialised and the interpreter kernels; expected state by direct formula (tests/test_jit_codegen.py has the CPU
+    version of this test)."""
+    from qls_b200.circuit import QuantumCircuit, UCRYGate
+
+    rng = np.random.default_rng(3)
+    n, ns = 20, 17
+    ang = rng.uniform(-3, 3, 2**ns)
+    front, back = QuantumCircuit(n), QuantumCircuit(n)
+    for q in range(n):
+        front.ry(float(rng.uniform(-2, 2)), q)
+    front.cx(2, 17), front.cp(0.3, 16, 4)
+    back.h(3), back.cx(3, 17), back.rz(0.7, 9), back.cx(17, 19)
+    qc = QuantumCircuit(n)
+    qc.compose(front, list(range(n)), inplace=True)
+    qc.append(UCRYGate(ang), [17] + list(range(ns)))
+    qc.compose(back, list(range(n)), inplace=True)
+    psi = numpy_sv.run(n, circuit_to_stream(front)).reshape(4, 2, 2**ns)  # [qubits 18-19, target, selectors]
+    c, s = np.cos(ang / 2), np.sin(ang / 2)
+    psi = np.stack([c * psi[:, 0] - s * psi[:, 1], s * psi[:, 0] + c * psi[:, 1]], axis=1).reshape(-1)
+    want = numpy_sv.run(n, circuit_to_stream(back), psi0=psi)
+    got, prog = _run(qc, jit_on=jit_on)
+    assert all(p.rs_stages > 0 for p in prog.lowered.pass_info)
+    assert np.max(np.abs(got - want)) <= TOL64

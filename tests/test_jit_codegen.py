@@ -169,3 +169,34 @@ def test_program_form_with_shared_gate_shapes(monkeypatch):
     assert any("qls_prog[" in s for s in srcs)
     got = run_program(low, form="jit")
     assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_multiplexer_over_seventeen_selectors():
+    """A multiplexed RY over MORE than 16 selector qubits (the ExactReciprocal of a sharded 34-36 qubit solve has 17-18
+    clock qubits) keeps a register-stage form: selectors inside the tile index the low table bits.  Expected state by
+    direct formula (the oracle's dense UCRY matrix would be 2^18 x 2^18)."""
+    from qls_b200.circuit import QuantumCircuit, UCRYGate
+
+    rng = np.random.default_rng(3)
+    n, ns = 18, 17
+    ang = rng.uniform(-3, 3, 2**ns)
+    front, back = QuantumCircuit(n), QuantumCircuit(n)
+    for q in range(n):
+        front.ry(float(rng.uniform(-2, 2)), q)
+    front.cx(2, 17), front.cp(0.3, 16, 4)
+    back.h(3), back.cx(3, 17), back.rz(0.7, 9)
+    qc = QuantumCircuit(n)
+    qc.compose(front, list(range(n)), inplace=True)
+    qc.append(UCRYGate(ang), [17] + list(range(ns)))  # qargs = [target, selector_0, ...]
+    qc.compose(back, list(range(n)), inplace=True)
+
+    psi = numpy_sv.run(n, circuit_to_stream(front)).reshape(2, 2**ns)  # [target, selectors]
+    c, s = np.cos(ang / 2), np.sin(ang / 2)
+    psi = np.stack([c * psi[0] - s * psi[1], s * psi[0] + c * psi[1]]).reshape(-1)
+    want = numpy_sv.run(n, circuit_to_stream(back), psi0=psi)
+
+    low = lower_circuit(qc, LoweringOptions(dtype="fp64"))
+    assert all(p.rs_stages > 0 for p in low.pass_info)
+    for form in ("rs", "jit"):
+        got = run_program(low, form=form)
+        assert np.max(np.abs(got - want)) <= 1e-12, form

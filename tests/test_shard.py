@@ -245,3 +245,33 @@ def test_gemm_register_is_pinned(world):
     gemms = [s for seg in plan.segments if seg.kind == "local" for s in seg.lowered.steps if s.kind == "gemm"]
     assert len(gemms) == 2 * hhl.nl and all(s.nb == 9 for s in gemms)
     assert all(plan.final_layout[q] == q for q in range(9))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_deferred_final_gates_fold_into_the_slice_reduction(world):
+    """Solver path: the final Hadamard of a clock qubit that is on a global position at the end is not applied; the
+    clock = 0 slice is the rank-weighted sum of the local slices (``solution_slice_plan``).  Same slice as the full state of
+    the oracle, fewer exchanged qubits than the full plan."""
+    from qls_b200.shard import solution_slice_plan
+
+    n = 13
+    qc = hhl_shaped_circuit(n)
+    nb = qc.qregs[0].size
+    want = numpy_sv.run(n, circuit_to_stream(qc))
+    full = plan_sharded(qc, world, LoweringOptions(**OPTS), protect_low=2)
+    plan = plan_sharded(qc, world, LoweringOptions(**OPTS), protect_low=2, defer_final_1q=True)
+    assert not full.deferred
+    if world > 2:
+        assert plan.deferred and plan.n_swaps < full.n_swaps
+    assert all(plan.final_layout[q] >= plan.n_local and nb <= q < n - 1 for q in plan.deferred)  # clock qubits, global at the end
+    engines = _run_fake(plan, world, chunk=1 << 20)
+    x = np.zeros(2**nb, dtype=complex)
+    p_flag = 0.0
+    for r, e in enumerate(engines):
+        sel, local, w = solution_slice_plan(plan, nb, r)
+        x[sel] += w * e.state[local]
+        gidx = np.arange(2**plan.n_local, dtype=np.int64) | (r << plan.n_local)
+        p_flag += float(np.sum(np.abs(e.state[((gidx >> plan.final_layout[n - 1]) & 1) == 1]) ** 2))
+    half = 2 ** (n - 1)
+    assert np.max(np.abs(x - want[half:half + 2**nb])) < 1e-12
+    assert abs(p_flag - float(np.sum(np.abs(want[half:]) ** 2))) < 1e-12  # P(flag = 1) does not see a unitary on the clock
