@@ -255,6 +255,10 @@ int qls_ipc_close(void* ptr);
 int qls_enable_peer_access(int device, int peer);
 int qls_swap_peer(void* state, void* peer_state, int n_local, int dtype, const int* qubits_host, int k,
                   uint64_t my_value_bits, uint64_t peer_value_bits, uint64_t begin, uint64_t count, void* stream);
+/* Stream-ordered copy between any two device buffers visible to this process, peer-mapped ones included (cudaMemcpyAsync,
+ * i.e. the copy engines: a chunk of a remap travels to the partner's receive slot without occupying SMs).  Remap transport of
+ * qls_b200/shard.py; no reference counterpart (the reference is single-process: hhl_qiskit_implementation.py:49). */
+int qls_copy_async(void* dst, const void* src, uint64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -129,6 +129,7 @@ SYMBOLS = {
     "qls_ipc_open": (_i, [_vp, _i, C.POINTER(C.c_void_p)]),
     "qls_ipc_close": (_i, [_vp]),
     "qls_swap_peer": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _u64, _vp]),
+    "qls_copy_async": (_i, [_vp, _vp, _u64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -166,6 +166,13 @@ extern "C" int qls_swap_peer(void* state, void* peer_state, int n_local, int dty
   return QLS_OK;
 }
 
+extern "C" int qls_copy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+  QLS_ARG(dst && src, "null pointer");
+  if (bytes == 0) return QLS_OK;
+  QLS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)));
+  return QLS_OK;
+}
+
 // kernels of `device` may dereference memory of `peer` (mapped through CUDA IPC) once this has succeeded
 extern "C" int qls_enable_peer_access(int device, int peer) {
   QLS_CUDA(cudaSetDevice(device));
