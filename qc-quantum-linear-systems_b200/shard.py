@@ -491,11 +491,31 @@ class CudaShardEngine:
             self.comm_stream = self.torch.cuda.Stream(device=t.device)
 
     def send_slot(self, partner: int, count: int, slot: int) -> None:
-        """Copy ``count`` amplitudes of my send slot into receive slot ``slot`` of ``partner`` (copy engines, current stream)."""
-        st = self.state
-        with self.torch.cuda.device(st.device):
-            self._abi.check(st.lib.qls_copy_async(self.peer_stage[partner][slot], self._send[slot].data_ptr(),
-                                                  count * self._send[slot].element_size(), self._stream()))
+        """Copy ``count`` amplitudes of my send slot into receive slot ``slot`` of ``partner`` (copy engines; ordered after the
+        work of the current stream, which waits for the copy).  QLS_REMAP_COPY_WAYS > 1 splits the copy over that many
+        streams so that several copy engines work on it."""
+        st, torch = self.state, self.torch
+        esz = self._send[slot].element_size()
+        ways = max(1, int(os.environ.get("QLS_REMAP_COPY_WAYS", "1")))
+        with torch.cuda.device(st.device):
+            if ways == 1 or count < (1 << 20):
+                self._abi.check(st.lib.qls_copy_async(self.peer_stage[partner][slot], self._send[slot].data_ptr(), count * esz,
+                                                      self._stream()))
+                return
+            if len(getattr(self, "_copy_streams", [])) < ways:
+                self._copy_streams = [torch.cuda.Stream(device=st.tensor.device) for _ in range(ways)]
+            cur = torch.cuda.current_stream()
+            ready = cur.record_event()
+            part = (count + ways - 1) // ways
+            for w in range(ways):
+                lo, hi = w * part, min(count, (w + 1) * part)
+                if lo >= hi:
+                    break
+                sw = self._copy_streams[w]
+                sw.wait_event(ready)
+                self._abi.check(st.lib.qls_copy_async(self.peer_stage[partner][slot] + lo * esz, self._send[slot].data_ptr() + lo * esz,
+                                                      (hi - lo) * esz, int(sw.cuda_stream)))
+                cur.wait_event(sw.record_event())
 
     def push(self, partner: int, lposs: Sequence[int], value: int, begin: int, count: int, slot: int) -> None:
         """Gather ``count`` amplitudes of my sub-block ``value`` straight into receive slot ``slot`` of ``partner`` (remote
