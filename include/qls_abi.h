@@ -214,9 +214,12 @@ int qls_reduce(const void* state, int n_local, int dtype, int kind, uint64_t a, 
 /* ---- dense controlled-e^{iAt} block as a complex GEMM on the FP64 tensor pipe -------------- */
 
 /* rows of psi.reshape(-1, 2^nb) whose global row index satisfies (row_index & ctrl_mask) ==
- * ctrl_val are replaced by row @ U^T (U row-major 2^nb x 2^nb, device, in `dtype`).  `scratch`
- * must hold as many amplitudes as there are selected rows * 2^nb.  [PhaseEstimation's
- * controlled-U^(2^j) blocks inside HHL.construct_circuit, hhl..:35-38] */
+ * ctrl_val are replaced by row @ U^T (U row-major 2^nb x 2^nb, device, in `dtype`).
+ *   scratch != NULL: out of place in chunks of QLS_GEMM_CHUNK_ROWS selected rows + copy-back; `scratch` holds
+ *                    min(selected rows, QLS_GEMM_CHUNK_ROWS) * 2^nb amplitudes (256 MiB at nb = 10, whatever the state size);
+ *   scratch == NULL: in place (complex128, nb <= 10): no second buffer at all, ~25 % slower (see csrc/ctrl_gemm.cu).
+ * [PhaseEstimation's controlled-U^(2^j) blocks inside HHL.construct_circuit, hhl..:35-38] */
+#define QLS_GEMM_CHUNK_ROWS (1u << 14)
 int qls_ctrl_gemm(void* state, void* scratch, int n_local, int dtype, int nb, uint64_t ctrl_mask, uint64_t ctrl_val,
                   uint64_t index_offset, const void* u_dev, void* stream);
 

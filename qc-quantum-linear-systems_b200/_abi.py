@@ -14,6 +14,7 @@ QLS_MAX_SEG, QLS_MAX_HIGH, QLS_MAX_FSEG = 6, 8, 16
 QLS_OP_FLAG_REAL, QLS_OP_FLAG_PARAM = 1, 2
 QLS_OP_FLAG_ATTACH_PRE, QLS_OP_FLAG_ATTACH_POST, QLS_MAX_ATTACH = 4, 8, 4
 QLS_RED_NORM_RANGE, QLS_RED_PROB_MASK, QLS_RED_EXPECT_Z, QLS_RED_INNER = 0, 1, 2, 3
+QLS_GEMM_CHUNK_ROWS = 1 << 14  # include/qls_abi.h
 QLS_REDUCE_WORKSPACE_BYTES = 64 * 1024
 UINT64_MAX = 2**64 - 1
 

@@ -35,6 +35,7 @@ struct QlsProgram {
   uint32_t n_passes, n_ops;
   QlsPass* passes_host;  // host copy (launch geometry is computed on the host)
   QlsOp* ops_dev;
+  QlsOp* ops_host;  // host copy of the sweep-form ops (the batched estimator splits a pass at its MATVEC ops)
   QlsRsOp* rs_ops_dev;
   uint32_t n_rs_ops;
   unsigned char* pool_dev;
@@ -118,3 +119,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+
+// rows r < total_rows of state.reshape(-1, 2^nb) (complex128) with (r & row_mask) == row_val are replaced by row @ U^T,
+// in place on the FP64 tensor pipe (ctrl_gemm.cu; 6 <= nb <= 10)
+int qls_gemm_rows_inplace(void* state, uint64_t total_rows, int nb, uint64_t row_mask, uint64_t row_val, const void* u_dev,
+                          cudaStream_t stream);

@@ -210,6 +210,8 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   p->pool_bytes = pool_bytes;
   p->passes_host = new QlsPass[n_passes ? n_passes : 1];
   p->ops_dev = nullptr;
+  p->ops_host = new QlsOp[n_ops ? n_ops : 1];
+  for (uint32_t i = 0; i < n_ops; ++i) p->ops_host[i] = ops_host[i];
   p->pool_dev = nullptr;
   p->rs_img_dev = nullptr;
   p->rs_img_off = nullptr;
@@ -222,6 +224,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
     if ((uint64_t)ps.op_begin + ps.op_count > n_ops) {
       qls_set_error("pass %u: op range outside program", i);
       delete[] p->passes_host;
+      delete[] p->ops_host;
       delete p;
       return QLS_ERR_ARG;
     }
@@ -235,6 +238,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
         if (op.tq[j] >= ps.tile_bits) {
           qls_set_error("pass %u op %u: target bit %d outside tile of %d bits", i, o, (int)op.tq[j], ps.tile_bits);
           delete[] p->passes_host;
+          delete[] p->ops_host;
           delete p;
           return QLS_ERR_ARG;
         }
@@ -243,6 +247,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
     if ((uint64_t)ps.rs_begin + ps.rs_count > n_rs_ops) {
       qls_set_error("pass %u: register-stage range outside program", i);
       delete[] p->passes_host;
+      delete[] p->ops_host;
       delete p;
       return QLS_ERR_ARG;
     }
@@ -277,6 +282,7 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
     if (p->rs_ops_dev) cudaFree(p->rs_ops_dev);
     if (p->pool_dev) cudaFree(p->pool_dev);
     delete[] p->passes_host;
+    delete[] p->ops_host;
     delete p;
     return e == cudaErrorMemoryAllocation ? QLS_ERR_NOMEM : QLS_ERR_CUDA;
   }
@@ -296,6 +302,7 @@ extern "C" int qls_program_destroy(QlsProgram* prog) {
   delete[] prog->rs_img_bytes;
   delete[] prog->rs_img_kr;
   delete[] prog->passes_host;
+  delete[] prog->ops_host;
   delete prog;
   return QLS_OK;
 }

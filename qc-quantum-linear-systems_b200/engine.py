@@ -6,6 +6,8 @@ scratch, the reduction workspace), exposing the current CUDA stream, and (in ``s
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import List, Optional, Sequence
 
@@ -192,8 +194,10 @@ class DeviceProgram:
                                                         s.pass_begin, s.pass_end, stream))
                 elif s.kind == "gemm":
                     n_rows_sel = 2 ** (state.n_local - s.nb - bin(s.ctrl_mask & (2**state.n_local - 1)).count("1"))
-                    scratch = state.scratch(n_rows_sel * 2**s.nb)
-                    _abi.check(self.lib.qls_ctrl_gemm(state.ptr, scratch.data_ptr(), state.n_local, self.abi_dtype, s.nb,
+                    # out of place through a bounded scratch (<= 2^14 rows) + copy-back; QLS_GEMM_INPLACE=1: no scratch at all
+                    in_place = lw.dtype == "fp64" and s.nb <= 10 and os.environ.get("QLS_GEMM_INPLACE", "0") == "1"
+                    scratch_ptr = None if in_place else state.scratch(min(n_rows_sel, _abi.QLS_GEMM_CHUNK_ROWS) * 2**s.nb).data_ptr()
+                    _abi.check(self.lib.qls_ctrl_gemm(state.ptr, scratch_ptr, state.n_local, self.abi_dtype, s.nb,
                                                       s.ctrl_mask, s.ctrl_val, state.index_offset,
                                                       self._gemm_mats[i].data_ptr(), stream))
                 elif s.kind == "init":
@@ -245,8 +249,10 @@ class DeviceProgram:
                     nbytes += sum(lw.pass_bytes(j, state.n_local) for j in range(s.pass_begin, s.pass_end))
                 elif s.kind == "gemm":
                     n_rows_sel = 2 ** (state.n_local - s.nb - bin(s.ctrl_mask & (2**state.n_local - 1)).count("1"))
-                    scratch = state.scratch(n_rows_sel * 2**s.nb)
-                    _abi.check(self.lib.qls_ctrl_gemm(state.ptr, scratch.data_ptr(), state.n_local, self.abi_dtype, s.nb,
+                    # out of place through a bounded scratch (<= 2^14 rows) + copy-back; QLS_GEMM_INPLACE=1: no scratch at all
+                    in_place = lw.dtype == "fp64" and s.nb <= 10 and os.environ.get("QLS_GEMM_INPLACE", "0") == "1"
+                    scratch_ptr = None if in_place else state.scratch(min(n_rows_sel, _abi.QLS_GEMM_CHUNK_ROWS) * 2**s.nb).data_ptr()
+                    _abi.check(self.lib.qls_ctrl_gemm(state.ptr, scratch_ptr, state.n_local, self.abi_dtype, s.nb,
                                                       s.ctrl_mask, s.ctrl_val, state.index_offset,
                                                       self._gemm_mats[i].data_ptr(), stream))
             torch.cuda.synchronize()

@@ -13,6 +13,8 @@ go through the streaming engine one by one.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -67,7 +69,8 @@ class BatchProgram:
 
         self.num_qubits = circuit.num_qubits
         self.num_parameters = circuit.num_parameters
-        self.lowered = lower_circuit(circuit, LoweringOptions(dtype=precision, batch=True, max_fuse_qubits=3))
+        fuse_q = int(os.environ.get("QLS_BATCH_FUSE", "2"))
+        self.lowered = lower_circuit(circuit, LoweringOptions(dtype=precision, batch=True, max_fuse_qubits=fuse_q))
         if self.lowered.n_passes != 1:
             raise _abi.QlsError("batch lowering must produce exactly one pass")
         self.program = DeviceProgram(self.lowered, device)

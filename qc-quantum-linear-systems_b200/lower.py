@@ -536,6 +536,7 @@ class _Emitter:
         self.cur_high: set = set()
         # qubits known to be |0> (never acted on non-diagonally since the state was prepared); None: unknown
         self.zero: Optional[set] = None
+        self.bzero: Optional[set] = None  # batch mode: qubits still |0> (see add)
 
     # -- pool -----------------------------------------------------------------------------
     def _pool_add(self, arr: np.ndarray) -> int:
@@ -568,6 +569,18 @@ class _Emitter:
         if self.opts.batch:
             if b.kind == "init":
                 raise NotImplementedError("state preparation inside a batched circuit")
+            # Batched circuits start from |0...0>.  A qubit nothing has acted on non-diagonally yet is still |0>: every
+            # amplitude with that bit set is zero, so a block that does not use the qubit may skip them -- expressed as a
+            # control on value 0 (exact; the Hadamard-test ancilla stays |0> through the whole ansatz: half the work)
+            if self.bzero is None:
+                self.bzero = set(range(self.n))
+            if b.kind in ("dense", "param", "gemm"):
+                extra = {q: 0 for q in self.bzero if q not in b.support}
+                if any(v == 1 and q in self.bzero for q, v in b.controls.items()):
+                    return  # controlled on a qubit that is still |0>: the identity
+                if extra:
+                    b = dataclasses.replace(b, controls={**b.controls, **extra})
+            self.bzero -= set(b.touched)
             self.cur.append(b)
             self.cur_high |= set(b.touched)
             return

@@ -170,8 +170,40 @@ def test_hhl_toy_models_vs_golden(cuda_device, name):
     assert math.isclose(res.euclidean_norm, numpy_sv.hhl_norm(want, n, hhl.scaling), rel_tol=1e-12)
 
 
+@pytest.mark.parametrize("in_place", [False, True])
+@pytest.mark.parametrize("nb,n,ctrl", [(6, 22, (21,)), (7, 20, (9, 15)), (10, 22, ())])
+def test_ctrl_gemm_direct(cuda_device, nb, n, ctrl, in_place):
+    """qls_ctrl_gemm through the C ABI on a random state: out of place through the bounded scratch (nb = 6, n = 22: 2^15
+    selected rows = two chunks of QLS_GEMM_CHUNK_ROWS) and in place (scratch = NULL: thread-block clusters of 1, 2 and 8
+    CTAs), against rows @ U^T in NumPy."""
+    import torch
+
+    from qls_b200 import _abi
+    from qls_b200.engine import DeviceState
+
+    rng = np.random.default_rng(nb + n)
+    psi = rng.standard_normal(2**n) + 1j * rng.standard_normal(2**n)
+    psi /= np.linalg.norm(psi)
+    u = random_unitary(nb, rng)
+    mask = sum(1 << q for q in ctrl)
+    st = DeviceState(n, "fp64")
+    st.write(0, psi)
+    u_dev = torch.from_numpy(np.ascontiguousarray(u)).cuda()
+    rows_sel = 2 ** (n - nb - len(ctrl))
+    scratch = None if in_place else torch.empty(min(rows_sel, _abi.QLS_GEMM_CHUNK_ROWS) * 2**nb, dtype=torch.complex128, device="cuda")
+    _abi.check(st.lib.qls_ctrl_gemm(st.ptr, None if in_place else scratch.data_ptr(), n, st.abi_dtype, nb, mask, mask, 0,
+                                    u_dev.data_ptr(), int(torch.cuda.current_stream().cuda_stream)))
+    got = st.read()
+    want = psi.reshape(-1, 2**nb).copy()
+    rows = np.arange(2 ** (n - nb), dtype=np.int64) << nb
+    sel = (rows & mask) == mask
+    want[sel] = want[sel] @ u.T
+    assert np.max(np.abs(got - want.reshape(-1))) <= 1e-14
+
+
+@pytest.mark.parametrize("in_place", [False, True])
 @pytest.mark.parametrize("nb", [6, 10])
-def test_hhl_gemm_block_path(cuda_device, nb):
+def test_hhl_gemm_block_path(cuda_device, nb, in_place, monkeypatch):
     """Dense controlled-e^{iAt} blocks on the data register go through qls_ctrl_gemm.  nb = 10 is BASELINE.json
     configs[1] at its real size (tridiagonal N = 2**10, reference formula nl = 12, n = 23: 24 complex 1024x1024
     products on 2**22 rows each) against the closed-form state, at the north-star tolerance."""
@@ -180,6 +212,7 @@ def test_hhl_gemm_block_path(cuda_device, nb):
     from qls_b200.statevector import Statevector
     from qls_b200.toymodels import TridiagonalToeplitz
 
+    monkeypatch.setenv("QLS_GEMM_INPLACE", "1" if in_place else "0")  # both forms of qls_ctrl_gemm (csrc/ctrl_gemm.cu)
     model = TridiagonalToeplitz(nb)
     hhl = HHL(power_mode="eig")
     qc = hhl.construct_circuit(model.matrix_a, model.vector_b)
