@@ -470,7 +470,9 @@ def run_gpu(args):
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import run_configs
 
-                line["other_configs"] = {"hhl_tridiagonal_n23": run_configs.config2(), "vqls_batch_4096x10q": run_configs.config3()}
+                line["other_configs"] = {"hhl_tridiagonal_n23": run_configs.config2(), "vqls_batch_4096x10q": run_configs.config3(),
+                                         "e2e_plugin_hhl_tridiagonal_n23": run_configs.plugin_e2e(),
+                                         "hhl_shaped_n30_dense5": run_configs.config4_dense5()}
             except Exception as exc:  # never lose the headline line because a secondary config failed
                 line["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), file=json_out, flush=True)

@@ -57,12 +57,21 @@ class NumPyMatrix:
         self.mode = mode
         self._eig = None
 
+    def _is_hermitian(self) -> bool:
+        return bool(np.allclose(self.matrix, self.matrix.conj().T))
+
     def condition_bounds(self):
-        kappa = float(np.linalg.cond(self.matrix))
+        # Hermitian input (HHL requires it): singular values = |eigenvalues|, and the eigen-decomposition is needed for the
+        # evolution anyway -- np.linalg.cond (an SVD) and np.linalg.eigvals were 2.1 of the 3.1 s of construct_circuit at N = 2^10
+        if self._is_hermitian():
+            ev = np.abs(self._eigh()[0])
+            kappa = float(np.max(ev) / np.min(ev))
+        else:
+            kappa = float(np.linalg.cond(self.matrix))
         return kappa, kappa
 
     def eigs_bounds(self):
-        ev = np.abs(np.linalg.eigvals(self.matrix))
+        ev = np.abs(self._eigh()[0]) if self._is_hermitian() else np.abs(np.linalg.eigvals(self.matrix))
         return float(np.min(ev)), float(np.max(ev))
 
     def _eigh(self):
