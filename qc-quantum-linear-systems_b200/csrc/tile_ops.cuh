@@ -125,6 +125,69 @@ __device__ __forceinline__ void op_dense(V* __restrict__ sm, int T, const QlsOp&
   }
 }
 
+// ---- DENSE on 4 or 5 qubits with the matrix in __constant__ memory (complex128) ------------------------------
+// The generic form above fetches every matrix element with a per-thread load (one LDG per four DFMAs, 16-deep
+// accumulator blocks that spill at the 128-register bound).  Here the host copies the matrices of a pass's wide dense
+// blocks into a __constant__ table before the launch (stream ordered, like the register-stage kernel's pass image): the
+// element index is warp-uniform (row slice from the warp index, row and column from unrolled loops), so the FMAs take
+// their matrix operand through the uniform datapath, and R = 8 accumulators (S = 4 row slices for k = 5, 2 for k = 4)
+// fit the register budget.  One image per device at a time: the passes of a device are issued on ONE stream.
+#define QLS_HEAVY_CONST 3072  // complex128 elements: three 32 x 32 or twelve 16 x 16 matrices (48 KB of the 64 KB bank)
+#define QLS_MAX_HEAVY 12
+static __constant__ double2 c_heavy[QLS_HEAVY_CONST];
+
+template <int K, int S, int THREADS>
+__device__ __forceinline__ void op_dense_cm(double2* __restrict__ sm, int T, const QlsOp& op, uint32_t cbase, int tid) {
+  constexpr int D = 1 << K;
+  constexpr int R = D / S;
+  constexpr int GPI = THREADS / S;  // groups per iteration; GPI >= 32: the row slice is warp-uniform
+  static_assert(GPI % 32 == 0, "row slice must be warp-uniform");
+  const int ngroups = 1 << (T - K);
+  uint32_t bit[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) bit[j] = 1u << op.tq[j];
+  const uint32_t lc_mask = op.lc_mask, lc_val = op.lc_val;
+  const int h = __shfl_sync(0xffffffffu, tid / GPI, 0);  // (provably uniform: keeps the matrix index on the uniform datapath)
+  const double2* __restrict__ Mrow = c_heavy + cbase + ((h * R) << K);
+  for (int g0 = 0; g0 < ngroups; g0 += GPI) {
+    const int g = g0 + (tid % GPI);
+    bool active = g < ngroups;
+    uint32_t idx = 0;
+    if (active) {
+      idx = g;
+#pragma unroll
+      for (int j = 0; j < K; ++j) idx = insert_zero_bit(idx, op.tq[j]);
+      active = (idx & lc_mask) == lc_val;
+    }
+    double2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r].x = acc[r].y = 0;
+    if (active) {
+#pragma unroll 4
+      for (int c = 0; c < D; ++c) {
+        uint32_t off = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) off |= ((c >> j) & 1) ? bit[j] : 0u;
+        const double2 v = sm[idx | off];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cfma(acc[r], Mrow[(r << K) | c], v);
+      }
+    }
+    __syncthreads();  // every row slice has read the group's inputs
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = h * R + r;
+        uint32_t off = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) off |= ((row >> j) & 1) ? bit[j] : 0u;
+        sm[idx | off] = acc[r];
+      }
+    }
+    if (g0 + GPI < ngroups) __syncthreads();
+  }
+}
+
 // ---- DIAG: amp *= table[bits of the (global) index] (times any attached tables) --------------------
 template <typename V, int THREADS>
 __device__ __forceinline__ void op_diag(V* __restrict__ sm, int T, const QlsOp& op, const V* __restrict__ table,
@@ -177,10 +240,14 @@ __device__ __forceinline__ void op_muxry(V* __restrict__ sm, int T, const QlsOp&
 // ---- dispatcher ------------------------------------------------------------------------------------
 // Applies ops[0..n_ops) to the tile; every thread of the block must call it.  gbase = global index
 // of tile-local index 0 (external controls and table fields outside the tile are read from it).
+// heavy_off (optional): for the k >= 4 dense ops of the pass in order, the element offset of their matrix in c_heavy
+// (0xFFFF: not there, use the pool).
 template <typename V, int THREADS, bool HEAVY>
 __device__ __forceinline__ void apply_ops(V* __restrict__ sm, int T, const QlsOp* __restrict__ ops, int n_ops,
-                                          const unsigned char* __restrict__ pool, uint64_t gbase, int tid) {
+                                          const unsigned char* __restrict__ pool, uint64_t gbase, int tid,
+                                          const uint16_t* __restrict__ heavy_off = nullptr) {
   int o = 0;
+  int heavy_seen = 0;
   while (o < n_ops) {
     const QlsOp& op = ops[o];
     int n_att = 0;
@@ -188,6 +255,10 @@ __device__ __forceinline__ void apply_ops(V* __restrict__ sm, int T, const QlsOp
            (ops[o + 1 + n_att].flags & (QLS_OP_FLAG_ATTACH_PRE | QLS_OP_FLAG_ATTACH_POST)))
       ++n_att;
     const int next = o + 1 + n_att;
+    // ordinal among the pass's wide dense blocks (counted whether or not the block fires on this tile: the host numbers them all)
+    const bool wide = HEAVY && op.kind == QLS_OP_DENSE && !(op.flags & QLS_OP_FLAG_PARAM) && op.k >= 4;
+    const int my_heavy = heavy_seen;
+    if (wide) ++heavy_seen;
     if ((gbase & op.xc_mask) != op.xc_val) {  // block-uniform
       o = next;
       continue;
@@ -210,10 +281,19 @@ __device__ __forceinline__ void apply_ops(V* __restrict__ sm, int T, const QlsOp
             op_dense<V, 3, 1, THREADS, false>(sm, T, op, data, tid, att);
             break;
           case 4:
-            if (HEAVY) op_dense<V, 4, 1, THREADS, false>(sm, T, op, data, tid, att);
-            break;
           case 5:
-            if (HEAVY) op_dense<V, 5, 2, THREADS, false>(sm, T, op, data, tid, att);
+            if (HEAVY) {
+              const uint32_t co = (heavy_off && my_heavy < QLS_MAX_HEAVY) ? heavy_off[my_heavy] : 0xFFFFu;
+              if constexpr (sizeof(V) == 16) {
+                if (co != 0xFFFFu && n_att == 0) {
+                  if (op.k == 4) op_dense_cm<4, 2, THREADS>(reinterpret_cast<double2*>(sm), T, op, co, tid);
+                  else op_dense_cm<5, 4, THREADS>(reinterpret_cast<double2*>(sm), T, op, co, tid);
+                  break;
+                }
+              }
+              if (op.k == 4) op_dense<V, 4, 1, THREADS, false>(sm, T, op, data, tid, att);
+              else op_dense<V, 5, 2, THREADS, false>(sm, T, op, data, tid, att);
+            }
             break;
         }
         break;

@@ -16,6 +16,7 @@ struct TileLaunch {
   uint64_t index_offset;
   uint32_t n_ops;
   uint32_t pad;
+  uint16_t heavy_off[QLS_MAX_HEAVY];  // element offsets into c_heavy of the pass's k >= 4 dense matrices (0xFFFF: in the pool)
 };
 
 template <typename R, int THREADS, bool HEAVY>
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(THREADS, HEAVY ? 2 : 3)
   cp_async_wait<0>();
   __syncthreads();
 
-  apply_ops<V, THREADS, HEAVY>(sm, T, ops, (int)tl.n_ops, pool, base | tl.index_offset, tid);
+  apply_ops<V, THREADS, HEAVY>(sm, T, ops, (int)tl.n_ops, pool, base | tl.index_offset, tid, HEAVY ? tl.heavy_off : nullptr);
 
   for (int u = tid; u < units; u += THREADS) {
     const int i = u * APU;
@@ -93,6 +94,24 @@ static int launch_pass(const QlsProgram* prog, const QlsPass& p, void* state, in
   tl.fix_val = p.fix_val;
   tl.index_offset = index_offset;
   tl.n_ops = p.op_count;
+  for (int j = 0; j < QLS_MAX_HEAVY; ++j) tl.heavy_off[j] = 0xFFFFu;
+  if (HEAVY && sizeof(V) == 16) {
+    // matrices of the wide dense blocks -> __constant__ table (device to device, stream ordered)
+    uint32_t used = 0;
+    int seen = 0;
+    for (uint32_t o = p.op_begin; o < p.op_begin + p.op_count && seen < QLS_MAX_HEAVY; ++o) {
+      const QlsOp& op = prog->ops_host[o];
+      if (op.kind != QLS_OP_DENSE || (op.flags & QLS_OP_FLAG_PARAM) || op.k < 4) continue;
+      const uint32_t elems = 1u << (2 * op.k);
+      if (used + elems <= QLS_HEAVY_CONST) {
+        QLS_CUDA(cudaMemcpyToSymbolAsync(c_heavy, prog->pool_dev + op.pool_off, (size_t)elems * 16, (size_t)used * 16,
+                                         cudaMemcpyDeviceToDevice, stream));
+        tl.heavy_off[seen] = (uint16_t)used;
+        used += elems;
+      }
+      ++seen;
+    }
+  }
   const int fixed = __builtin_popcountll(p.fix_mask);
   const int free_bits = n_local - p.tile_bits - fixed;
   QLS_ARG(free_bits >= 0 && free_bits < 31, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);

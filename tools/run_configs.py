@@ -121,7 +121,7 @@ def config4_dense5(n=30, repeats=2):
             "passes_on_the_sweep_kernel": int(sweep_passes), "p_flag1": p_flag, "norm_sq": norm_sq,
             "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": 36.8, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / 36.8, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
-                         "note": "5-qubit dense blocks on csrc/tile_pass.cu (no register-stage / specialised form yet)"}}
+                         "note": "5-qubit dense blocks on csrc/tile_pass.cu (matrix in __constant__ memory, 8 accumulators per thread; no register-stage / specialised form yet)"}}
 
 
 def plugin_e2e(nb=10, repeats=2):
