@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(THREADS)
 // (HEAVY = the pass holds a dense block on 4 or 5 qubits: their register-blocked code costs 252 registers per thread, i.e.
 // ONE resident CTA per SM -- an 8 x slower ansatz segment when it is compiled in without being needed)
 template <int THREADS, bool HEAVY>
-__global__ void __launch_bounds__(THREADS, HEAVY ? 1 : 3)
+__global__ void __launch_bounds__(THREADS, HEAVY ? 1 : 768 / THREADS)
     qls_batch_segment_kernel(const QlsOp* __restrict__ ops, int o_begin, int o_end, const unsigned char* __restrict__ pool, int n,
                              int z_qubit, const double* __restrict__ params, int n_params, double2* __restrict__ scratch,
                              int load_lo, int load_k, int store_lo, int store_k, double* __restrict__ out) {
@@ -279,7 +279,9 @@ static bool batch_gemm_form(const QlsProgram* prog, const QlsPass& p, int n_qubi
 
 static int batch_expect_z_gemm(const QlsProgram* prog, const QlsPass& p, int n, int z_qubit, const double* params_dev,
                                uint32_t n_circuits, uint32_t n_params, double* out_dev, cudaStream_t s) {
-  constexpr int THREADS = 256;
+  // 128 threads per circuit: the per-op overhead (record decode, dispatch, block barrier) is paid per warp, the arithmetic
+  // of a 10-qubit state is a few instructions per thread either way
+  constexpr int THREADS = 128;
   auto kern = (p.pad & 1u) ? qls_batch_segment_kernel<THREADS, true> : qls_batch_segment_kernel<THREADS, false>;
   const size_t smem = ((size_t)16 << n) + (size_t)16 * p.op_count;  // state + (cos, sin) of the parameterised rotations
   QLS_ARG(smem <= 200 * 1024, "state does not fit shared memory (%zu bytes)", smem);
