@@ -425,17 +425,26 @@ def run_gpu(args):
             sent = st["remap_bytes_sent_per_gpu"]
             ms = getattr(solver, "remap_ms", 0.0)
             p2p = bool(getattr(solver.engine, "peers", None))
-            if p2p:  # one swap kernel per pairwise round
+            push = os.environ.get("QLS_REMAP_PUSH", "1")
+            if p2p and push == "0":  # one swap kernel per pairwise round
                 launches_per_step += sum(2 ** len(sg.pairs) - 1 for sg in solver.plan.segments if sg.kind == "swap")
+                how = "peer memory (CUDA IPC over NVLink): one in-place swap kernel per pairwise round"
+            elif p2p:  # one gather + one scatter kernel per chunk; the transfer itself is a copy-engine copy
+                launches_per_step += 2 * max(1, sent // (S * solver.runner.chunk))
+                how = ("peer memory (CUDA IPC over NVLink): gather kernel -> copy engines into the partner's receive slot -> "
+                       "scatter kernel, 2 GiB chunks, two slots, two streams" if push != "sm" else
+                       "peer memory (CUDA IPC over NVLink): remote stores from the gather kernel, scatter kernel")
             else:  # one pack + one unpack per chunk on the wire
                 launches_per_step += 2 * max(1, sent // (S * solver.runner.chunk))
+                how = "pack + NCCL send/recv + unpack, chunked"
+            fallback = getattr(solver, "transport_fallback", None)
             remap = {"remapped_qubits_per_step": st["remaps"], "exchanges_per_step": st["remap_exchanges"],
                      "bytes_sent_per_gpu": sent, "ms_per_step": ms,
                      "achieved_gbs_per_direction": (sent / (ms * 1e-3) / 1e9) if ms else None, "peak": 770.0,
                      "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
                      "frac": (sent / (ms * 1e-3) / 1e9 / 770.0) if ms else None,
-                     "transport": "peer memory (CUDA IPC over NVLink): one swap kernel per pairwise round" if p2p
-                                  else "pack + NCCL send/recv + unpack, chunked",
+                     "transport": how, "transport_fallback_reason": fallback,
+                     "deferred_final_gates": len(getattr(solver.plan, "deferred", {}) or {}),
                      "includes": "a k-qubit exchange is one all-to-all of 2^k - 1 pairwise rounds, device barriers included; "
                                  "not overlapped with compute"}
         line = {
