@@ -288,18 +288,38 @@ bool qls_jit_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_in
   return prog->jit && prog->jit[pass_index] && p.tile_bits == 12 && n_local >= p.tile_bits;
 }
 
+static int g_grid_reserve = 0;
+// SMs the specialised pass kernels leave free (a persistent CTA per SM otherwise holds every SM for the whole pass, and the
+// barrier kernel of an exchange running beside it would wait for the pass to end)
+extern "C" int qls_set_pass_grid_reserve(int n_sms) {
+  QLS_ARG(n_sms >= 0 && n_sms < 64, "bad SM reserve %d", n_sms);
+  g_grid_reserve = n_sms;
+  return QLS_OK;
+}
+
 int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
-                        uint64_t index_offset, cudaStream_t stream) {
+                        uint64_t index_offset, cudaStream_t stream, int sel_pos, int sel_val) {
   Driver* d = driver();
   const QlsJitKernel* k = prog->jit[pass_index];
   const int fixed = __builtin_popcountll(p.fix_mask);
   const int free_bits = n_local - p.tile_bits - fixed;
   QLS_ARG(free_bits >= 0 && free_bits < 40, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
   uint64_t n_tiles = 1ull << free_bits;
+  uint32_t sel_ord = 64u, sel_v = 0u;
+  if (sel_pos >= 0) {  // restrict to the tiles whose state-index bit sel_pos equals sel_val: find its bit in the tile ordinal
+    int ord = -1;
+    for (int j = 0; j < p.n_fseg; ++j)
+      if (sel_pos >= p.fseg[j].dst && sel_pos < p.fseg[j].dst + p.fseg[j].width) ord = p.fseg[j].src + (sel_pos - p.fseg[j].dst);
+    QLS_ARG(ord >= 0 && free_bits >= 1, "pass %u: index bit %d is not a free position of the pass", pass_index, sel_pos);
+    sel_ord = (uint32_t)ord;
+    sel_v = (uint32_t)(sel_val & 1);
+    n_tiles >>= 1;
+  }
   static int sm_count[64] = {0};
   if (!sm_count[prog->device & 63])
     QLS_CUDA(cudaDeviceGetAttribute(&sm_count[prog->device & 63], cudaDevAttrMultiProcessorCount, prog->device));
-  uint64_t grid = (uint64_t)sm_count[prog->device & 63];
+  uint64_t grid = (uint64_t)(sm_count[prog->device & 63] - g_grid_reserve);
+  if (grid < 1) grid = 1;
   if (grid > n_tiles) grid = n_tiles;
   const void* pool = prog->pool_dev;
   alignas(64) CUtensorMap tmap;
@@ -309,7 +329,7 @@ int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_
     if (erc) return erc;
   }
   void* trace = g_trace_dev;
-  void* args[] = {&state, &index_offset, &n_tiles, &pool, &tmap, &trace};
+  void* args[] = {&state, &index_offset, &n_tiles, &pool, &tmap, &trace, &sel_ord, &sel_v};
   const int rc = d->LaunchKernel(k->fn, (unsigned)grid, 1, 1, k->threads, 1, 1, k->smem, stream, args, nullptr);
   if (rc) {
     qls_set_error("cuLaunchKernel (pass %u): %s", pass_index, cu_err(d, rc));

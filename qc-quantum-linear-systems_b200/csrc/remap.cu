@@ -173,6 +173,26 @@ extern "C" int qls_copy_async(void* dst, const void* src, uint64_t bytes, void* 
   return QLS_OK;
 }
 
+extern "C" int qls_copy2d_async(void* dst, uint64_t dst_pitch, const void* src, uint64_t src_pitch, uint64_t width_bytes,
+                                uint64_t height, void* stream) {
+  QLS_ARG(dst && src, "null pointer");
+  if (width_bytes == 0 || height == 0) return QLS_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (height == 1 || (dst_pitch == width_bytes && src_pitch == width_bytes)) {
+    QLS_CUDA(cudaMemcpyAsync(dst, src, width_bytes * height, cudaMemcpyDefault, s));
+    return QLS_OK;
+  }
+  const uint64_t max_pitch = 0x7fffffffull;  // cudaMemcpy2D's pitch limit; wider strides: one copy per row (rows are huge then)
+  if (dst_pitch > max_pitch || src_pitch > max_pitch) {
+    for (uint64_t r = 0; r < height; ++r)
+      QLS_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + r * dst_pitch, static_cast<const char*>(src) + r * src_pitch, width_bytes,
+                               cudaMemcpyDefault, s));
+    return QLS_OK;
+  }
+  QLS_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDefault, s));
+  return QLS_OK;
+}
+
 // kernels of `device` may dereference memory of `peer` (mapped through CUDA IPC) once this has succeeded
 extern "C" int qls_enable_peer_access(int device, int peer) {
   QLS_CUDA(cudaSetDevice(device));

@@ -27,7 +27,11 @@ static_assert(QLS_GROUPS * QLS_GROUP_THREADS * QLS_CONSUMER_REGS + 128 * 24 <= Q
 
 extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
     qls_rs2_pass(V* __restrict__ state, const u64 index_offset, const u64 n_tiles, const unsigned char* __restrict__ pool,
-                 const __grid_constant__ QlsTensorMap tmap, u64* __restrict__ qls_trace) {
+                 const __grid_constant__ QlsTensorMap tmap, u64* __restrict__ qls_trace, const u32 sel_pos, const u32 sel_val) {
+  // sel_pos < 64: the launch covers HALF of the pass -- the tiles whose ordinal has bit sel_pos equal to sel_val (n_tiles is
+  // already halved): ordinal t of the launch is ordinal qls_tile_sel(t) of the pass.  A sharded state runs the passes next to
+  // an exchange on one half of the shard while the other half is on the wire (qls_b200/shard.py).
+#define qls_tile_sel(t) (sel_pos < 64u ? ((((t) >> sel_pos) << (sel_pos + 1u)) | ((u64)sel_val << sel_pos) | ((t) & ((1ull << sel_pos) - 1ull))) : (t))
   extern __shared__ unsigned char qls_smem_raw[];
   // 1024-byte alignment: the tensor-map swizzle pattern is a function of the shared-memory address
   unsigned char* const qls_smem = qls_smem_raw + ((1024u - (qls_smem_u32(qls_smem_raw) & 1023u)) & 1023u);
@@ -63,7 +67,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       QLS_PTR(20, qq);
       qls_mbar_wait(done + b, (u32)(qq / QLS_NBUF) & 1u);
       QLS_PTR(21, qq);
-      const u64 base = qls_tile_base((u64)blockIdx.x + qq * gridDim.x);
+      const u64 base = qls_tile_base(qls_tile_sel((u64)blockIdx.x + qq * gridDim.x));
       if (!qls_tile_idle(base | index_offset)) {
         unsigned char* buf = qls_smem + b * QLS_BUF_BYTES;
 #ifdef QLS_EXP_NOLOAD  // timing experiment: no global traffic at all
@@ -86,7 +90,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       if (tile >= n_tiles) break;
       if (q >= QLS_NBUF) retire(q - QLS_NBUF);
       const u32 b = (u32)(q % QLS_NBUF);
-      const u64 base = qls_tile_base(tile);
+      const u64 base = qls_tile_base(qls_tile_sel(tile));
       const bool idle = qls_tile_idle(base | index_offset);
       if (lane == 0) {
         // Publish which tile this round of the buffer belongs to BEFORE arming it.  A parity wait cannot tell round
@@ -149,7 +153,7 @@ extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
       }
       qls_mbar_wait(full + b, (q / QLS_NBUF) & 1u);
       QLS_TR(2);
-      const u64 gbase = qls_tile_base(tile) | index_offset;
+      const u64 gbase = qls_tile_base(qls_tile_sel(tile)) | index_offset;
       if (!qls_tile_idle(gbase)) {
         qls_tile_body(reinterpret_cast<V*>(qls_smem + b * QLS_BUF_BYTES), gbase, tid, qls_group, pool, qls_trace, qls_q, qls_cursor);
         qls_fence_proxy_async();  // the bulk store reads this group's shared-memory writes through the async proxy

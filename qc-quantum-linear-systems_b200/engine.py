@@ -140,6 +140,7 @@ class DeviceProgram:
         # fall-back to the interpreter kernels; QLS_JIT=0 selects those on purpose.
         self.jit_passes = 0
         self.jit_modes = {}
+        self.jit_attached = set()  # pass indices that have a specialised kernel
         from . import jit
 
         if jit.enabled() and lowered.dtype == "fp64" and lowered.n_local >= jit.min_qubits():
@@ -147,6 +148,7 @@ class DeviceProgram:
                 for cp in jit.compile_program(lowered):
                     mode = jit.attach(self.lib, self.handle, cp, lowered.n_local)
                     self.jit_passes += 1
+                    self.jit_attached.add(cp.index)
                     self.jit_modes[mode] = self.jit_modes.get(mode, 0) + 1
         self._gemm_mats = {}
         cdt = torch.complex128 if lowered.dtype == "fp64" else torch.complex64
@@ -167,9 +169,12 @@ class DeviceProgram:
         except Exception:
             pass
 
-    def run(self, state: DeviceState, initialise: bool = True) -> None:
-        """Evolve ``state`` (|0...0> unless ``initialise`` is False) through the whole program."""
+    def run(self, state: DeviceState, initialise: bool = True, first_pass: int = 0, last_pass: Optional[int] = None) -> None:
+        """Evolve ``state`` (|0...0> unless ``initialise`` is False) through the whole program.  ``first_pass`` / ``last_pass``
+        clip the tile passes to ``[first_pass, last_pass)`` (the sharded solver runs the passes next to an exchange itself,
+        half a shard at a time: ``run_pass_part``)."""
         lw = self.lowered
+        last_pass = lw.n_passes if last_pass is None else last_pass
         if state.n_local != lw.n_local:
             raise ValueError(f"state has {state.n_local} local qubits, program expects {lw.n_local}")
         steps = lw.steps
@@ -190,8 +195,9 @@ class DeviceProgram:
             for i in range(first, len(steps)):
                 s = steps[i]
                 if s.kind == "passes":
-                    _abi.check(self.lib.qls_program_run(self.handle, state.ptr, state.n_local, state.index_offset,
-                                                        s.pass_begin, s.pass_end, stream))
+                    lo, hi = max(s.pass_begin, first_pass), min(s.pass_end, last_pass)
+                    if lo < hi:
+                        _abi.check(self.lib.qls_program_run(self.handle, state.ptr, state.n_local, state.index_offset, lo, hi, stream))
                 elif s.kind == "gemm":
                     n_rows_sel = 2 ** (state.n_local - s.nb - bin(s.ctrl_mask & (2**state.n_local - 1)).count("1"))
                     # out of place through a bounded scratch (<= 2^14 rows) + copy-back; QLS_GEMM_INPLACE=1: no scratch at all
@@ -204,6 +210,17 @@ class DeviceProgram:
                     raise NotImplementedError("state preparation is only supported as the first operation")
                 else:
                     raise ValueError(s.kind)
+
+    def run_pass_part(self, state: DeviceState, pass_index: int, sel_pos: int, sel_val: int) -> None:
+        """Pass ``pass_index`` on the half of the state whose index bit ``sel_pos`` equals ``sel_val`` (current stream)."""
+        with _torch().cuda.device(self.device):
+            _abi.check(self.lib.qls_program_run_part(self.handle, state.ptr, state.n_local, state.index_offset, int(pass_index),
+                                                     int(sel_pos), int(sel_val), _stream_ptr()))
+
+    def free_positions(self, pass_index: int) -> List[int]:
+        """State-index positions a pass neither transforms nor fixes (it can run on one value of any of them)."""
+        p = self.lowered.passes[pass_index]
+        return [p.fseg[j].dst + w for j in range(p.n_fseg) for w in range(p.fseg[j].width)]
 
     def run_each_pass_timed(self, state: DeviceState):
         """Debug aid: per-pass milliseconds (one CUDA event pair per tile pass)."""

@@ -77,7 +77,34 @@ def _relabel(b: Block, phys: Sequence[int]) -> Block:
 
 
 def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[LoweringOptions] = None,
-                 protect_low: int = 8, fold_first_gates: bool = True, defer_final_1q: bool = False) -> ShardedPlan:
+                 protect_low: int = 8, fold_first_gates: bool = True, defer_final_1q: bool = False,
+                 contiguous_evict: Any = "auto") -> ShardedPlan:
+    """``contiguous_evict``: "auto" plans twice -- evicting the farthest-touched qubits wherever they sit, and evicting them
+    from consecutive positions even if one of them is touched a little sooner ("force") -- and keeps the second plan if it
+    does not exchange more amplitudes or run more passes (its exchanges are pitched copies: no gather / scatter kernels)."""
+    if contiguous_evict == "auto":
+        a = _plan_sharded(circuit, world_size, opts, protect_low, fold_first_gates, defer_final_1q, True)
+        b = _plan_sharded(circuit, world_size, opts, protect_low, fold_first_gates, defer_final_1q, "force")
+
+        def cost(pl: ShardedPlan):
+            return (sum(1.0 - 0.5 ** len(sg.pairs) for sg in pl.segments if sg.kind == "swap"),
+                    sum(sg.lowered.n_passes for sg in pl.segments if sg.kind == "local"))
+
+        def n_contig(pl: ShardedPlan) -> int:
+            return sum(1 for sg in pl.segments if sg.kind == "swap" and _is_window(sg.pairs))
+
+        return b if cost(b) <= cost(a) and n_contig(b) > n_contig(a) else a
+    return _plan_sharded(circuit, world_size, opts, protect_low, fold_first_gates, defer_final_1q, contiguous_evict)
+
+
+def _is_window(pairs: Sequence[Tuple[int, int]]) -> bool:
+    """The local positions of an exchange are consecutive."""
+    ls = sorted(l for _, l in pairs)
+    return all(b - a == 1 for a, b in zip(ls, ls[1:]))
+
+
+def _plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[LoweringOptions], protect_low: int,
+                  fold_first_gates: bool, defer_final_1q: bool, contiguous_evict: Any) -> ShardedPlan:
     """``defer_final_1q``: an uncontrolled one-qubit gate that is the LAST block referring to its qubit at all is not applied
     if the qubit sits on a global position when the gate is reached; it is returned in ``ShardedPlan.deferred`` instead.
     For a consumer that only needs the state projected on one value of that qubit (the HHL solver path reads the
@@ -207,14 +234,33 @@ def plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Loweri
             # evict: local qubits with the farthest next touch, high positions first, never the low run
             cands = [q for q in range(n) if protect_low <= phys[q] < n_local and q not in b.touched and q not in gemm_pinned]
             cands.sort(key=lambda q: (-next_touch(q, i), -phys[q]))
-            pairs = []
+            chosen: List[Tuple[int, int]] = []  # (incoming qubit, evicted qubit)
             for qin in incoming:
-                if not cands:
+                if len(chosen) == len(cands):
                     break
-                qout = cands[0]
+                qout = cands[len(chosen)]
                 if qin not in need_global and next_touch(qout, i) <= next_touch(qin, i):
                     break  # not worth it
-                cands.pop(0)
+                chosen.append((qin, qout))
+            if contiguous_evict and len(chosen) > 1:
+                # Same number of qubits, but evicted from CONSECUTIVE local positions [p, p + k): a sub-block of the
+                # exchange is then rows of 2^p amplitudes at one pitch -- one pitched copy per chunk for the copy engines,
+                # no gather / scatter kernels.  Window = the one whose soonest-touched member is touched latest (never
+                # sooner than the soonest-touched qubit of the greedy choice, or the greedy choice stands).
+                k = len(chosen)
+                ok = {phys[q]: q for q in cands}
+                floor = min(next_touch(qo, i) for _, qo in chosen)
+                best = None
+                for p0 in range(protect_low, n_local - k + 1):
+                    if all(p0 + j in ok for j in range(k)):
+                        key = (min(next_touch(ok[p0 + j], i) for j in range(k)), p0)
+                        if best is None or key > best[0]:
+                            best = (key, p0)
+                if best is not None and (best[0][0] >= floor or contiguous_evict == "force"):
+                    window = [ok[best[1] + j] for j in range(k)]
+                    chosen = [(qin, qout) for (qin, _), qout in zip(chosen, window)]
+            pairs = []
+            for qin, qout in chosen:
                 pairs.append((phys[qin], phys[qout]))
                 phys[qin], phys[qout] = phys[qout], phys[qin]
             if any(phys[q] >= n_local for q in b.touched):
@@ -296,7 +342,13 @@ class ShardedRunner:
         k = len(pairs)
         block = 2 ** (self.plan.n_local - k)
         if getattr(self.engine, "peers", None) and os.environ.get("QLS_REMAP_PUSH", "1") != "0":
-            self._swap_many_push(gbits, lposs, k, block)
+            if self.ce_capable(lposs):
+                torch = self.engine.torch
+                main = torch.cuda.current_stream()
+                for ev in self.exchange_ce(pairs, [main.record_event()]):
+                    main.wait_event(ev)
+            else:
+                self._swap_many_push(gbits, lposs, k, block)
             return
         if getattr(self.engine, "peers", None):
             # peer-memory path: one swap kernel per round and GPU on disjoint halves of the element range, the
@@ -345,6 +397,83 @@ class ShardedRunner:
             self.engine.unpack(inc, lposs, value, begin, count)
             inflight = nxt
 
+
+    def ce_capable(self, lposs: Sequence[int]) -> bool:
+        """Exchanges whose local positions are consecutive can be done by the copy engines alone (pitched copies)."""
+        ls = sorted(lposs)
+        return (os.environ.get("QLS_REMAP_CE", "1") != "0" and hasattr(self.engine, "copy_rows")
+                and all(b - a == 1 for a, b in zip(ls, ls[1:])))
+
+    def exchange_ce(self, pairs: Sequence[Tuple[int, int]], ready: Sequence[Any], half_bit: Optional[int] = None) -> List[Any]:
+        """Copy-engine exchange of ``k`` CONSECUTIVE local positions ``[p, p + k)``: the sub-block with local bits ``v`` is rows
+        of ``2^p`` amplitudes at a pitch of ``2^(p+k)``, so a chunk of it is ONE pitched copy.  Per (round, chunk) job:
+        my sub-block chunk -> the partner's receive slot (peer copy, stream c1) -> barrier -> receive slot -> the rows the
+        chunk vacated (local pitched copy, stream c2).  No kernel touches the amplitudes, so local passes can run beside it.
+
+        ``ready``: one event per part; the jobs of part ``i`` start after ``ready[i]``.  With ``half_bit`` (a bit of the
+        sub-block's element index, >= log2(chunk)) there are two parts: elements with that bit 0, then those with it 1 --
+        the caller runs passes on the half of the shard that is not on the wire.  Returns one event per part: the part has
+        been scattered.  All ranks enqueue the same job order; the main stream is not touched."""
+        torch, dist, eng = self.engine.torch, self.dist, self.engine
+        order = sorted(range(len(pairs)), key=lambda j: pairs[j][1])
+        gbits = [pairs[j][0] for j in order]
+        lposs = [pairs[j][1] for j in order]
+        k, p = len(pairs), lposs[0]
+        block = 2 ** (self.plan.n_local - k)
+        esz = eng.state.tensor.element_size()
+        chunk = min(self.chunk, eng._recv[0].numel(), block)
+        n_parts = 2 if half_bit is not None else 1
+        assert len(ready) == n_parts and (half_bit is None or (1 << half_bit) >= chunk)
+        jobs = []
+        for part in range(n_parts):
+            for d in range(1, 2**k):
+                partner = self.rank
+                for j in range(k):
+                    if (d >> j) & 1:
+                        partner ^= 1 << gbits[j]
+                value = sum(((partner >> gbits[j]) & 1) << j for j in range(k))
+                for b in range(0, block, chunk):
+                    if half_bit is None or ((b >> half_bit) & 1) == part:
+                        jobs.append((part, partner, value, b, min(chunk, block - b)))
+
+        def geometry(value: int, begin: int, count: int) -> Tuple[int, int, int, int]:
+            """(byte offset in the state, pitch, width, height) of elements [begin, begin + count) of sub-block ``value``."""
+            row = 1 << p
+            if count <= row:  # inside one row
+                off = (((begin >> p) << (p + k)) | (value << p) | (begin & (row - 1))) * esz
+                return off, count * esz, count * esz, 1
+            off = (((begin >> p) << (p + k)) | (value << p)) * esz
+            return off, (row << k) * esz, row * esz, count >> p
+
+        c1, c2 = eng.comm_stream, eng.scatter_stream
+        base = eng.state.ptr
+        scattered: List[Any] = []
+        done: List[Any] = [None] * n_parts
+        started = [False] * n_parts
+        for i, (part, partner, value, begin, count) in enumerate(jobs):
+            slot = i & 1
+            off, pitch, width, height = geometry(value, begin, count)
+            with torch.cuda.stream(c1):
+                if not started[part]:
+                    c1.wait_event(ready[part])  # the passes before the exchange have produced this part
+                    started[part] = True
+                eng.copy_rows(eng.peer_stage[partner][slot], width, base + off, pitch, width, height)
+                if scattered:
+                    c1.wait_event(scattered[-1])  # my scatter of job i - 1 precedes barrier i (the partner reuses that slot for i + 1)
+                eng.device_barrier(dist)
+                arrived = c1.record_event()
+            with torch.cuda.stream(c2):
+                c2.wait_event(arrived)
+                eng.copy_rows(base + off, pitch, eng._recv[slot].data_ptr(), width, width, height)
+                scattered.append(c2.record_event())
+            done[part] = scattered[-1]  # c2 is in order: the last scatter of a part implies the earlier ones
+            self.bytes_sent += count * esz
+        with torch.cuda.stream(c1):  # nobody starts the next exchange's copies before every scatter of this one is done
+            for ev in scattered[-2:]:
+                c1.wait_event(ev)
+            eng.device_barrier(dist)
+            closed = c1.record_event()
+        return [ev if ev is not None else closed for ev in done[:-1]] + [closed]
 
     def _swap_many_push(self, gbits: Sequence[int], lposs: Sequence[int], k: int, block: int) -> None:
         """Push-only exchange over peer memory.  Job (round, chunk): every rank gathers the chunk of the sub-block that
@@ -489,6 +618,13 @@ class CudaShardEngine:
         with self.torch.cuda.device(self.state.device):
             self._tiny = self.torch.zeros(1, dtype=self.torch.float32, device=t.device)
             self.comm_stream = self.torch.cuda.Stream(device=t.device)
+            self.scatter_stream = self.torch.cuda.Stream(device=t.device)
+
+    def copy_rows(self, dst: int, dst_pitch: int, src: int, src_pitch: int, width: int, height: int) -> None:
+        """Pitched copy between device addresses (own or peer-mapped) by the copy engines, on the current stream."""
+        st = self.state
+        with self.torch.cuda.device(st.device):
+            self._abi.check(st.lib.qls_copy2d_async(dst, dst_pitch, src, src_pitch, width, height, self._stream()))
 
     def send_slot(self, partner: int, count: int, slot: int) -> None:
         """Copy ``count`` amplitudes of my send slot into receive slot ``slot`` of ``partner`` (copy engines; ordered after the
