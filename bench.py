@@ -196,7 +196,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 
 
-def sharded_parity_check(world: int, rank: int, local_rank: int, precision: str, n_local: int = 26) -> dict:
+def sharded_parity_check(world: int, rank: int, local_rank: int, precision: str, n_local: int = 26,
+                         chunk_amps: int = 1 << 20) -> dict:
     """Before anything is timed: the same generator at ``n_local + log2(world)`` qubits, sharded over all ranks and
     unsharded on rank 0, same right-hand side -- solution slice, P(flag = 1) and |x|^2 must agree to 1e-12 (fp64).
     Every rank raises if they do not."""
@@ -213,8 +214,12 @@ def sharded_parity_check(world: int, rank: int, local_rank: int, precision: str,
     nb = qc.qregs[0].size
     b = np.random.default_rng(7).standard_normal(2**nb) + 0j
     b /= np.linalg.norm(b)
-    sharded = ShardedShapedSolver(qc, nb, precision=precision, device=local_rank)
+    # (small chunks: at this size the exchanges then split into halves like the full-size ones do, so the passes
+    # overlapped with them -- half a shard at a time -- are part of what is checked)
+    sharded = ShardedShapedSolver(qc, nb, precision=precision, device=local_rank, chunk_amps=chunk_amps)
     xs, ps, ns = sharded.solve(b)
+    overlapped = {str(j): {"split_position": v[0], "passes_before": len(v[2]), "passes_after": len(v[3])}
+                  for j, v in (getattr(sharded, "_overlap", None) or {}).items()}
     transport = "peer memory" if getattr(sharded.engine, "peers", None) else "nccl"
     out = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")
     if rank == 0:
@@ -231,7 +236,8 @@ def sharded_parity_check(world: int, rank: int, local_rank: int, precision: str,
     dx, dp, dn, xmax = (float(v) for v in out.tolist())
     tol = 1e-12 if precision == "fp64" else 1e-5
     res = {"n_qubits": n, "ranks": world, "shard_parity_max_abs": max(dx, dp, dn), "x_slice_max_abs": dx, "p_flag1_abs": dp,
-           "norm_sq_abs": dn, "x_slice_max_amplitude": xmax, "tolerance": tol, "transport": transport}
+           "norm_sq_abs": dn, "x_slice_max_amplitude": xmax, "tolerance": tol, "transport": transport,
+           "exchanges_overlapped_with_passes": overlapped}
     if not max(dx, dp, dn) <= tol:
         raise SystemExit(f"sharded / unsharded mismatch: {res}")
     return res

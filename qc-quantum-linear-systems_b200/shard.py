@@ -33,6 +33,12 @@ from ._abi import QlsError
 from .circuit import QuantumCircuit, flatten
 from .lower import Block, LoweredProgram, LoweringOptions, fuse, lower_blocks, normalise
 
+def _check(rc: int) -> None:
+    from . import _abi
+
+    _abi.check(rc)
+
+
 # --------------------------------------------------------------------------------------
 # planning
 # --------------------------------------------------------------------------------------
@@ -770,12 +776,98 @@ class ShardedShapedSolver:
                 amps = np.asarray(self._init_amps if b_host is None else b_host)
                 self.state.write(0, amps if factor == 1.0 else amps * factor)
 
+    # -- exchanges overlapped with the local passes on both sides of them ----------------------------------------------
+    def _plan_overlap(self) -> Dict[int, Tuple[int, int, List[int], List[int]]]:
+        """For every exchange that the copy engines can do alone: a local position ``h`` that neither the exchange nor the
+        passes next to it touch, the trailing passes of the segment before (``pa``) and the leading passes of the segment
+        after (``pb``) that leave ``h`` alone.  Those passes then run on the ``h = 0`` half of the shard and on the ``h = 1``
+        half separately, and each half is exchanged while the other one is being computed on:
+
+            pa on half 0 | pa on half 1  ||  exchange half 0 | exchange half 1  ||  pb on half 0 | pb on half 1
+                         '-- overlaps --'                    '------------- overlaps -------------'
+
+        Returns {segment index of the exchange: (h, bit of h in the sub-block's element index, pa, pb)}."""
+        segs = self.plan.segments
+        nl = self.plan.n_local
+        out: Dict[int, Tuple[int, int, List[int], List[int]]] = {}
+        if os.environ.get("QLS_SHARD_OVERLAP", "1") == "0" or not getattr(self.engine, "peers", None) \
+                or os.environ.get("QLS_REMAP_PUSH", "1") == "0":
+            return out
+        chunk = min(self.runner.chunk, self.engine._recv[0].numel())
+        used_prefix: Dict[int, int] = {}  # local segment index -> passes taken as "pb" of the exchange before it
+        for j, seg in enumerate(segs):
+            if seg.kind != "swap" or j == 0 or j + 1 >= len(segs):
+                continue
+            lposs = sorted(l for _, l in seg.pairs)
+            if not self.runner.ce_capable(lposs):
+                continue
+            la, lb = segs[j - 1].lowered, segs[j + 1].lowered
+            pa_prog, pb_prog = self.engine.programs[id(la)], self.engine.programs[id(lb)]
+            # trailing passes of A / leading passes of B (only if the segment ends / starts with tile passes)
+            a_rng = range(la.steps[-1].pass_begin, la.steps[-1].pass_end) if la.steps and la.steps[-1].kind == "passes" else range(0)
+            b_rng = range(lb.steps[0].pass_begin, lb.steps[0].pass_end) if lb.steps and lb.steps[0].kind == "passes" else range(0)
+            a_lo = max(a_rng.start, used_prefix.get(j - 1, 0)) if len(a_rng) else 0
+            best = None
+            for h in range(nl):
+                if h in lposs:
+                    continue
+                ebit = h - sum(1 for l in lposs if l < h)
+                if (1 << ebit) < chunk or (1 << ebit) >= (1 << (nl - len(lposs))):
+                    continue
+                pa: List[int] = []
+                for pi in reversed(a_rng):
+                    if pi < a_lo or pi not in pa_prog.jit_attached or h not in pa_prog.free_positions(pi):
+                        break
+                    pa.insert(0, pi)
+                pb: List[int] = []
+                for pi in b_rng:
+                    if pi not in pb_prog.jit_attached or h not in pb_prog.free_positions(pi):
+                        break
+                    pb.append(pi)
+                score = sum(la.pass_bytes(pi) for pi in pa) + sum(lb.pass_bytes(pi) for pi in pb)
+                if score > 0 and (best is None or score > best[0]):
+                    best = (score, h, ebit, pa, pb)
+            if best is not None:
+                out[j] = best[1:]
+                used_prefix[j + 1] = (best[4][-1] + 1) if best[4] else 0
+        return out
+
     def _run_segments(self) -> None:
-        for seg in self.plan.segments:
+        segs = self.plan.segments
+        if getattr(self, "_overlap", None) is None:
+            self._overlap = self._plan_overlap()
+        ov = self._overlap
+        torch = self.engine.torch
+        lib = self.state.lib
+        for j, seg in enumerate(segs):
             if seg.kind == "local":
-                self.engine.programs[id(seg.lowered)].run(self.state, initialise=False)  # state prepared by _prepare
-            else:
-                self.runner.swap_many([(gpos - self.plan.n_local, lpos) for gpos, lpos in seg.pairs])
+                prog = self.engine.programs[id(seg.lowered)]
+                first = (ov[j - 1][3][-1] + 1) if (j - 1) in ov and ov[j - 1][3] else 0          # run as "pb" of the exchange before
+                last = ov[j + 1][2][0] if (j + 1) in ov and ov[j + 1][2] else None               # run as "pa" of the exchange after
+                prog.run(self.state, initialise=False, first_pass=first, last_pass=last)         # state prepared by _prepare
+                continue
+            pairs = [(gpos - self.plan.n_local, lpos) for gpos, lpos in seg.pairs]
+            if j not in ov:
+                self.runner.swap_many(pairs)
+                continue
+            h, ebit, pa, pb = ov[j]
+            prog_a, prog_b = self.engine.programs[id(segs[j - 1].lowered)], self.engine.programs[id(segs[j + 1].lowered)]
+            main = torch.cuda.current_stream()
+            _check(lib.qls_set_pass_grid_reserve(1))  # the exchange's barrier kernel needs an SM beside the persistent pass kernels
+            try:
+                ready = []
+                for v in (0, 1):
+                    for pi in pa:
+                        prog_a.run_pass_part(self.state, pi, h, v)
+                    ready.append(main.record_event())
+                done = self.runner.exchange_ce(pairs, ready, half_bit=ebit)
+                for v in (0, 1):
+                    main.wait_event(done[v])
+                    for pi in pb:
+                        prog_b.run_pass_part(self.state, pi, h, v)
+                main.wait_event(done[1])
+            finally:
+                _check(lib.qls_set_pass_grid_reserve(0))
 
     def run_device(self, b_device=None) -> None:
         self._prepare(b_device=b_device)

@@ -86,3 +86,45 @@ def test_sharded_hhl_shaped_matches_oracle(cuda_device, tmp_path, world, p2p):
     p_flag, norm_sq = np.load(tmp_path / "scalars.npy")
     assert abs(p_flag - numpy_sv.prob_mask(want, half, half)) < 1e-12
     assert abs(norm_sq - np.sum(np.abs(want[half: half + 2**nb]) ** 2)) < 1e-13
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device(f"cuda:{rank}"))
+    try:
+        import bench
+
+        res = bench.sharded_parity_check(world, rank, rank, "fp64", n_local=22, chunk_amps=1 << 15)
+        if rank == 0:
+            import json
+
+            with open(os.path.join(out_dir, "parity.json"), "w") as fh:
+                json.dump(res, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchanges_overlapped_with_passes(cuda_device, tmp_path, world):
+    """At 22 local qubits the passes run on the specialised kernels and the exchanges split into halves: the passes on both
+    sides of an exchange run half a shard at a time while the other half is on the wire (ShardedShapedSolver._run_segments).
+    Sharded vs single-GPU solver on the same right-hand side, 1e-12; at least one exchange must actually be overlapped."""
+    import json
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29700 + (os.getpid() + world) % 2000
+    mp.spawn(_overlap_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = json.load(open(tmp_path / "parity.json"))
+    assert res["shard_parity_max_abs"] <= 1e-12
+    assert res["exchanges_overlapped_with_passes"], res
