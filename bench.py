@@ -218,7 +218,7 @@ def sharded_parity_check(world: int, rank: int, local_rank: int, precision: str,
     # overlapped with them -- half a shard at a time -- are part of what is checked)
     sharded = ShardedShapedSolver(qc, nb, precision=precision, device=local_rank, chunk_amps=chunk_amps)
     xs, ps, ns = sharded.solve(b)
-    overlapped = {str(j): {"split_position": v[0], "passes_before": len(v[2]), "passes_after": len(v[3])}
+    overlapped = {str(j): {"split_positions": list(v[0]), "parts": 1 << len(v[0]), "passes_before": len(v[2]), "passes_after": len(v[3])}
                   for j, v in (getattr(sharded, "_overlap", None) or {}).items()}
     transport = "peer memory" if getattr(sharded.engine, "peers", None) else "nccl"
     out = torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}")

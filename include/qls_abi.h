@@ -267,12 +267,12 @@ int qls_copy_async(void* dst, const void* src, uint64_t bytes, void* stream);
  * slot and scatter the received one, no kernel involved. */
 int qls_copy2d_async(void* dst, uint64_t dst_pitch, const void* src, uint64_t src_pitch, uint64_t width_bytes, uint64_t height,
                      void* stream);
-/* One pass of a program on the half of the state whose index bit `sel_pos` is `sel_val` (specialised kernels only, else
- * QLS_ERR_UNSUPPORTED), and the number of SMs the specialised pass kernels leave free: the pieces with which qls_b200/shard.py
+/* One pass of a program on the half of the state whose index bit `sel_pos` is `sel_val` -- with `sel_pos2` >= 0 on the quarter
+ * whose bit `sel_pos2` is `sel_val2` as well -- (specialised kernels only, else QLS_ERR_UNSUPPORTED), and the number of SMs the specialised pass kernels leave free: the pieces with which qls_b200/shard.py
  * overlaps an exchange with the local passes on both sides of it.  Same reference call as qls_program_run
  * (hhl_qiskit_implementation.py:49). */
 int qls_program_run_part(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset, uint32_t pass_index, int sel_pos,
-                         int sel_val, void* stream);
+                         int sel_val, int sel_pos2, int sel_val2, void* stream);
 int qls_set_pass_grid_reserve(int n_sms);
 
 #ifdef __cplusplus

@@ -132,7 +132,7 @@ SYMBOLS = {
     "qls_swap_peer": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int), _i, _u64, _u64, _u64, _u64, _vp]),
     "qls_copy_async": (_i, [_vp, _vp, _u64, _vp]),
     "qls_copy2d_async": (_i, [_vp, _u64, _vp, _u64, _u64, _u64, _vp]),
-    "qls_program_run_part": (_i, [_vp, _vp, _i, _u64, C.c_uint32, _i, _i, _vp]),
+    "qls_program_run_part": (_i, [_vp, _vp, _i, _u64, C.c_uint32, _i, _i, _i, _i, _vp]),
     "qls_set_pass_grid_reserve": (_i, [_i]),
 }
 

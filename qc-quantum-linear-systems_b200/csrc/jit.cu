@@ -298,22 +298,40 @@ extern "C" int qls_set_pass_grid_reserve(int n_sms) {
 }
 
 int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
-                        uint64_t index_offset, cudaStream_t stream, int sel_pos, int sel_val) {
+                        uint64_t index_offset, cudaStream_t stream, int sel_pos, int sel_val, int sel_pos2, int sel_val2) {
   Driver* d = driver();
   const QlsJitKernel* k = prog->jit[pass_index];
   const int fixed = __builtin_popcountll(p.fix_mask);
   const int free_bits = n_local - p.tile_bits - fixed;
   QLS_ARG(free_bits >= 0 && free_bits < 40, "pass geometry: n_local=%d tile_bits=%d fixed=%d", n_local, p.tile_bits, fixed);
   uint64_t n_tiles = 1ull << free_bits;
-  uint32_t sel_ord = 64u, sel_v = 0u;
-  if (sel_pos >= 0) {  // restrict to the tiles whose state-index bit sel_pos equals sel_val: find its bit in the tile ordinal
-    int ord = -1;
-    for (int j = 0; j < p.n_fseg; ++j)
-      if (sel_pos >= p.fseg[j].dst && sel_pos < p.fseg[j].dst + p.fseg[j].width) ord = p.fseg[j].src + (sel_pos - p.fseg[j].dst);
-    QLS_ARG(ord >= 0 && free_bits >= 1, "pass %u: index bit %d is not a free position of the pass", pass_index, sel_pos);
-    sel_ord = (uint32_t)ord;
-    sel_v = (uint32_t)(sel_val & 1);
-    n_tiles >>= 1;
+  // restrict to the tiles whose state-index bits sel_pos (, sel_pos2) have the given values: find their bits in the tile ordinal
+  uint32_t sel_ord[2] = {64u, 64u}, sel_v[2] = {0u, 0u};
+  {
+    const int pos[2] = {sel_pos, sel_pos2}, val[2] = {sel_val, sel_val2};
+    int n_sel = 0;
+    for (int s = 0; s < 2; ++s) {
+      if (pos[s] < 0) continue;
+      int ord = -1;
+      for (int j = 0; j < p.n_fseg; ++j)
+        if (pos[s] >= p.fseg[j].dst && pos[s] < p.fseg[j].dst + p.fseg[j].width) ord = p.fseg[j].src + (pos[s] - p.fseg[j].dst);
+      QLS_ARG(ord >= 0, "pass %u: index bit %d is not a free position of the pass", pass_index, pos[s]);
+      sel_ord[n_sel] = (uint32_t)ord;
+      sel_v[n_sel] = (uint32_t)(val[s] & 1);
+      ++n_sel;
+    }
+    QLS_ARG(free_bits >= n_sel, "pass %u: too few free positions", pass_index);
+    if (n_sel == 2) {
+      QLS_ARG(sel_ord[0] != sel_ord[1], "pass %u: the two selection bits coincide", pass_index);
+      if (sel_ord[0] > sel_ord[1]) {  // the kernel inserts the lower ordinal bit first
+        const uint32_t o = sel_ord[0], v = sel_v[0];
+        sel_ord[0] = sel_ord[1];
+        sel_v[0] = sel_v[1];
+        sel_ord[1] = o;
+        sel_v[1] = v;
+      }
+    }
+    n_tiles >>= n_sel;
   }
   static int sm_count[64] = {0};
   if (!sm_count[prog->device & 63])
@@ -329,7 +347,7 @@ int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_
     if (erc) return erc;
   }
   void* trace = g_trace_dev;
-  void* args[] = {&state, &index_offset, &n_tiles, &pool, &tmap, &trace, &sel_ord, &sel_v};
+  void* args[] = {&state, &index_offset, &n_tiles, &pool, &tmap, &trace, &sel_ord[0], &sel_v[0], &sel_ord[1], &sel_v[1]};
   const int rc = d->LaunchKernel(k->fn, (unsigned)grid, 1, 1, k->threads, 1, 1, k->smem, stream, args, nullptr);
   if (rc) {
     qls_set_error("cuLaunchKernel (pass %u): %s", pass_index, cu_err(d, rc));

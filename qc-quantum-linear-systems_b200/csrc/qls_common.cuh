@@ -59,7 +59,8 @@ int qls_launch_rs_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_i
 void qls_jit_release(QlsProgram* prog);
 bool qls_jit_eligible(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, int n_local);
 int qls_launch_jit_pass(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, void* state, int n_local,
-                        uint64_t index_offset, cudaStream_t stream, int sel_pos = -1, int sel_val = 0);
+                        uint64_t index_offset, cudaStream_t stream, int sel_pos = -1, int sel_val = 0, int sel_pos2 = -1,
+                        int sel_val2 = 0);
 
 // ---- complex arithmetic on double2 / float2 -----------------------------------------------------
 template <typename R>

@@ -27,11 +27,18 @@ static_assert(QLS_GROUPS * QLS_GROUP_THREADS * QLS_CONSUMER_REGS + 128 * 24 <= Q
 
 extern "C" __global__ void __launch_bounds__(QLS_BLOCK_THREADS, 1)
     qls_rs2_pass(V* __restrict__ state, const u64 index_offset, const u64 n_tiles, const unsigned char* __restrict__ pool,
-                 const __grid_constant__ QlsTensorMap tmap, u64* __restrict__ qls_trace, const u32 sel_pos, const u32 sel_val) {
-  // sel_pos < 64: the launch covers HALF of the pass -- the tiles whose ordinal has bit sel_pos equal to sel_val (n_tiles is
-  // already halved): ordinal t of the launch is ordinal qls_tile_sel(t) of the pass.  A sharded state runs the passes next to
-  // an exchange on one half of the shard while the other half is on the wire (qls_b200/shard.py).
-#define qls_tile_sel(t) (sel_pos < 64u ? ((((t) >> sel_pos) << (sel_pos + 1u)) | ((u64)sel_val << sel_pos) | ((t) & ((1ull << sel_pos) - 1ull))) : (t))
+                 const __grid_constant__ QlsTensorMap tmap, u64* __restrict__ qls_trace, const u32 sel_pos, const u32 sel_val,
+                 const u32 sel_pos2, const u32 sel_val2) {
+  // sel_pos < 64: the launch covers a HALF (with sel_pos2 < 64 as well: a QUARTER) of the pass -- the tiles whose ordinal has
+  // bit sel_pos equal to sel_val (and bit sel_pos2 > sel_pos equal to sel_val2); n_tiles is already reduced: ordinal t of the
+  // launch is ordinal qls_tile_sel(t) of the pass.  A sharded state runs the passes next to an exchange on one part of the
+  // shard while another part is on the wire (qls_b200/shard.py).
+#define qls_ins_bit(t, pos, val) ((((t) >> (pos)) << ((pos) + 1u)) | ((u64)(val) << (pos)) | ((t) & ((1ull << (pos)) - 1ull)))
+  auto qls_tile_sel = [=](u64 t) -> u64 {
+    if (sel_pos < 64u) t = qls_ins_bit(t, sel_pos, sel_val);
+    if (sel_pos2 < 64u) t = qls_ins_bit(t, sel_pos2, sel_val2);
+    return t;
+  };
   extern __shared__ unsigned char qls_smem_raw[];
   // 1024-byte alignment: the tensor-map swizzle pattern is a function of the shared-memory address
   unsigned char* const qls_smem = qls_smem_raw + ((1024u - (qls_smem_u32(qls_smem_raw) & 1023u)) & 1023u);

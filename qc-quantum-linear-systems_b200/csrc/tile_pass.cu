@@ -154,10 +154,12 @@ extern "C" int qls_set_use_jit(int on) {
 // One pass restricted to the half of the state whose index bit `sel_pos` equals `sel_val` (a position the pass neither
 // transforms nor fixes).  Specialised kernels only: QLS_ERR_UNSUPPORTED otherwise, and the caller runs the pass whole.
 extern "C" int qls_program_run_part(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset, uint32_t pass_index,
-                                    int sel_pos, int sel_val, void* stream) {
+                                    int sel_pos, int sel_val, int sel_pos2, int sel_val2, void* stream) {
   QLS_ARG(prog && state, "null program or state");
   QLS_ARG(pass_index < prog->n_passes, "pass %u outside program of %u", pass_index, prog->n_passes);
   QLS_ARG(sel_pos >= 0 && sel_pos < n_local && (sel_val == 0 || sel_val == 1), "bad selection bit %d = %d", sel_pos, sel_val);
+  QLS_ARG(sel_pos2 < n_local && sel_pos2 != sel_pos && (sel_val2 == 0 || sel_val2 == 1), "bad second selection bit %d = %d", sel_pos2,
+          sel_val2);
   QLS_CUDA(cudaSetDevice(prog->device));
   const QlsPass& p = prog->passes_host[pass_index];
   int rc = validate_pass(p, n_local, prog->dtype);
@@ -167,7 +169,7 @@ extern "C" int qls_program_run_part(const QlsProgram* prog, void* state, int n_l
     return QLS_ERR_UNSUPPORTED;
   }
   return qls_launch_jit_pass(prog, p, pass_index, state, n_local, index_offset, reinterpret_cast<cudaStream_t>(stream), sel_pos,
-                             sel_val);
+                             sel_val, sel_pos2 < 0 ? -1 : sel_pos2, sel_val2);
 }
 
 extern "C" int qls_program_run(const QlsProgram* prog, void* state, int n_local, uint64_t index_offset,

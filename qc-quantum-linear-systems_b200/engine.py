@@ -9,7 +9,7 @@ from __future__ import annotations
 import os
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -211,11 +211,13 @@ class DeviceProgram:
                 else:
                     raise ValueError(s.kind)
 
-    def run_pass_part(self, state: DeviceState, pass_index: int, sel_pos: int, sel_val: int) -> None:
-        """Pass ``pass_index`` on the half of the state whose index bit ``sel_pos`` equals ``sel_val`` (current stream)."""
+    def run_pass_part(self, state: DeviceState, pass_index: int, sel: Sequence[Tuple[int, int]]) -> None:
+        """Pass ``pass_index`` on the part of the state whose index bits ``pos`` equal ``val`` for the one or two ``(pos, val)``
+        of ``sel`` (current stream)."""
+        (p1, v1), (p2, v2) = sel[0], (sel[1] if len(sel) > 1 else (-1, 0))
         with _torch().cuda.device(self.device):
             _abi.check(self.lib.qls_program_run_part(self.handle, state.ptr, state.n_local, state.index_offset, int(pass_index),
-                                                     int(sel_pos), int(sel_val), _stream_ptr()))
+                                                     int(p1), int(v1), int(p2), int(v2), _stream_ptr()))
 
     def free_positions(self, pass_index: int) -> List[int]:
         """State-index positions a pass neither transforms nor fixes (it can run on one value of any of them)."""

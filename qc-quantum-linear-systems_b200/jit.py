@@ -35,7 +35,7 @@ KERNEL_NAME = "qls_rs2_pass"
 T = 12  # tile bits of the specialised kernels (complex128)
 KR = 4  # register qubits per thread
 THREADS = 2 * 256 + 128  # two consumer groups + the producer warpgroup
-GEN_VERSION = 23  # bump when the generated code or the runtime headers change meaning
+GEN_VERSION = 24  # bump when the generated code or the runtime headers change meaning
 
 
 # --------------------------------------------------------------------------------------

@@ -410,16 +410,17 @@ class ShardedRunner:
         return (os.environ.get("QLS_REMAP_CE", "1") != "0" and hasattr(self.engine, "copy_rows")
                 and all(b - a == 1 for a, b in zip(ls, ls[1:])))
 
-    def exchange_ce(self, pairs: Sequence[Tuple[int, int]], ready: Sequence[Any], half_bit: Optional[int] = None) -> List[Any]:
+    def exchange_ce(self, pairs: Sequence[Tuple[int, int]], ready: Sequence[Any], part_bits: Sequence[int] = ()) -> List[Any]:
         """Copy-engine exchange of ``k`` CONSECUTIVE local positions ``[p, p + k)``: the sub-block with local bits ``v`` is rows
         of ``2^p`` amplitudes at a pitch of ``2^(p+k)``, so a chunk of it is ONE pitched copy.  Per (round, chunk) job:
         my sub-block chunk -> the partner's receive slot (peer copy, stream c1) -> barrier -> receive slot -> the rows the
         chunk vacated (local pitched copy, stream c2).  No kernel touches the amplitudes, so local passes can run beside it.
 
-        ``ready``: one event per part; the jobs of part ``i`` start after ``ready[i]``.  With ``half_bit`` (a bit of the
-        sub-block's element index, >= log2(chunk)) there are two parts: elements with that bit 0, then those with it 1 --
-        the caller runs passes on the half of the shard that is not on the wire.  Returns one event per part: the part has
-        been scattered.  All ranks enqueue the same job order; the main stream is not touched."""
+        ``ready``: one event per part; the jobs of part ``i`` start after ``ready[i]``.  ``part_bits`` (one or two bits of the
+        sub-block's element index, each >= log2(chunk)) cut the exchange into 2 or 4 parts: part ``i`` holds the elements whose
+        bit ``part_bits[j]`` equals bit ``j`` of ``i`` -- the caller runs passes on the parts of the shard that are not on the
+        wire.  Returns one event per part: the part has been scattered.  All ranks enqueue the same job order; the main
+        stream is not touched."""
         torch, dist, eng = self.engine.torch, self.dist, self.engine
         order = sorted(range(len(pairs)), key=lambda j: pairs[j][1])
         gbits = [pairs[j][0] for j in order]
@@ -428,8 +429,11 @@ class ShardedRunner:
         block = 2 ** (self.plan.n_local - k)
         esz = eng.state.tensor.element_size()
         chunk = min(self.chunk, eng._recv[0].numel(), block)
-        n_parts = 2 if half_bit is not None else 1
-        assert len(ready) == n_parts and (half_bit is None or (1 << half_bit) >= chunk)
+        n_parts = 1 << len(part_bits)
+        assert len(ready) == n_parts and all((1 << pb) >= chunk for pb in part_bits)
+
+        def part_of(b: int) -> int:
+            return sum(((b >> pb) & 1) << j for j, pb in enumerate(part_bits))
         jobs = []
         for part in range(n_parts):
             for d in range(1, 2**k):
@@ -439,7 +443,7 @@ class ShardedRunner:
                         partner ^= 1 << gbits[j]
                 value = sum(((partner >> gbits[j]) & 1) << j for j in range(k))
                 for b in range(0, block, chunk):
-                    if half_bit is None or ((b >> half_bit) & 1) == part:
+                    if part_of(b) == part:
                         jobs.append((part, partner, value, b, min(chunk, block - b)))
 
         def geometry(value: int, begin: int, count: int) -> Tuple[int, int, int, int]:
@@ -452,6 +456,7 @@ class ShardedRunner:
             return off, (row << k) * esz, row * esz, count >> p
 
         c1, c2 = eng.comm_stream, eng.scatter_stream
+        pair_sync = os.environ.get("QLS_REMAP_PAIR_SYNC", "1") != "0" and self.world > 2
         base = eng.state.ptr
         scattered: List[Any] = []
         done: List[Any] = [None] * n_parts
@@ -465,8 +470,14 @@ class ShardedRunner:
                     started[part] = True
                 eng.copy_rows(eng.peer_stage[partner][slot], width, base + off, pitch, width, height)
                 if scattered:
-                    c1.wait_event(scattered[-1])  # my scatter of job i - 1 precedes barrier i (the partner reuses that slot for i + 1)
-                eng.device_barrier(dist)
+                    c1.wait_event(scattered[-1])  # my scatter of job i - 1 precedes sync i (the receive slot of job i + 1 is that one)
+                # sync i tells me that job i has arrived and the rank I send job i + 1 to that its slot is free: with the same
+                # partner for both a pairwise hand-shake will do (a barrier over all ranks makes every job wait for the
+                # slowest pair: 511 GB/s at 8 GPUs against 667 at 2); the last job of a round needs everybody
+                if pair_sync and i + 1 < len(jobs) and jobs[i + 1][1] == partner:
+                    eng.pair_barrier(dist, partner)
+                else:
+                    eng.device_barrier(dist)
                 arrived = c1.record_event()
             with torch.cuda.stream(c2):
                 c2.wait_event(arrived)
@@ -673,6 +684,17 @@ class CudaShardEngine:
     def device_barrier(self, dist: Any) -> None:
         dist.all_reduce(self._tiny)  # stream ordered on every rank: nobody passes before everybody's earlier kernels are done
 
+    def pair_barrier(self, dist: Any, partner: int) -> None:
+        """Stream-ordered hand-shake with ONE rank (4-byte send + receive): neither side passes before the other's earlier work
+        on its stream is done."""
+        if not hasattr(self, "_tiny_rx"):
+            self._tiny_rx = self.torch.zeros_like(self._tiny)
+        ops = [dist.P2POp(dist.isend, self._tiny, partner), dist.P2POp(dist.irecv, self._tiny_rx, partner)]
+        if self.rank > partner:
+            ops.reverse()
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
     def swap_peer(self, partner: int, lposs: Sequence[int], my_value: int, peer_value: int, begin: int, count: int) -> None:
         import ctypes as C
 
@@ -777,22 +799,23 @@ class ShardedShapedSolver:
                 self.state.write(0, amps if factor == 1.0 else amps * factor)
 
     # -- exchanges overlapped with the local passes on both sides of them ----------------------------------------------
-    def _plan_overlap(self) -> Dict[int, Tuple[int, int, List[int], List[int]]]:
-        """For every exchange that the copy engines can do alone: a local position ``h`` that neither the exchange nor the
-        passes next to it touch, the trailing passes of the segment before (``pa``) and the leading passes of the segment
-        after (``pb``) that leave ``h`` alone.  Those passes then run on the ``h = 0`` half of the shard and on the ``h = 1``
-        half separately, and each half is exchanged while the other one is being computed on:
+    def _plan_overlap(self) -> Dict[int, Tuple[List[int], List[int], List[int], List[int]]]:
+        """For every exchange that the copy engines can do alone: one or two local positions ``h`` that neither the exchange nor
+        the passes next to it touch, the trailing passes of the segment before (``pa``) and the leading passes of the segment
+        after (``pb``) that leave them alone.  Those passes then run on one part of the shard at a time (``h = 0`` / ``h = 1``
+        halves, or the four quarters of two positions), and each part is exchanged while others are being computed on:
 
-            pa on half 0 | pa on half 1  ||  exchange half 0 | exchange half 1  ||  pb on half 0 | pb on half 1
-                         '-- overlaps --'                    '------------- overlaps -------------'
+            pa on part 0 | pa on part 1 | ...   ||   exchange part 0 | exchange part 1 | ...   ||   pb on part 0 | pb on part 1 ...
+                         '------ overlaps ------'                    '------------------ overlaps -----------------'
 
-        Returns {segment index of the exchange: (h, bit of h in the sub-block's element index, pa, pb)}."""
+        Returns {segment index of the exchange: (positions, their bits in the sub-block's element index, pa, pb)}."""
         segs = self.plan.segments
         nl = self.plan.n_local
-        out: Dict[int, Tuple[int, int, List[int], List[int]]] = {}
+        out: Dict[int, Tuple[List[int], List[int], List[int], List[int]]] = {}
         if os.environ.get("QLS_SHARD_OVERLAP", "1") == "0" or not getattr(self.engine, "peers", None) \
                 or os.environ.get("QLS_REMAP_PUSH", "1") == "0":
             return out
+        max_pos = 2 if os.environ.get("QLS_SHARD_OVERLAP", "1") != "2way" else 1
         chunk = min(self.runner.chunk, self.engine._recv[0].numel())
         used_prefix: Dict[int, int] = {}  # local segment index -> passes taken as "pb" of the exchange before it
         for j, seg in enumerate(segs):
@@ -807,26 +830,43 @@ class ShardedShapedSolver:
             a_rng = range(la.steps[-1].pass_begin, la.steps[-1].pass_end) if la.steps and la.steps[-1].kind == "passes" else range(0)
             b_rng = range(lb.steps[0].pass_begin, lb.steps[0].pass_end) if lb.steps and lb.steps[0].kind == "passes" else range(0)
             a_lo = max(a_rng.start, used_prefix.get(j - 1, 0)) if len(a_rng) else 0
-            best = None
+            free_a = {pi: set(pa_prog.free_positions(pi)) for pi in a_rng if pi in pa_prog.jit_attached}
+            free_b = {pi: set(pb_prog.free_positions(pi)) for pi in b_rng if pi in pb_prog.jit_attached}
+            cands = []
             for h in range(nl):
-                if h in lposs:
-                    continue
                 ebit = h - sum(1 for l in lposs if l < h)
-                if (1 << ebit) < chunk or (1 << ebit) >= (1 << (nl - len(lposs))):
-                    continue
+                if h not in lposs and chunk <= (1 << ebit) < (1 << (nl - len(lposs))):
+                    cands.append((h, ebit))
+
+            def runs(hs):
                 pa: List[int] = []
                 for pi in reversed(a_rng):
-                    if pi < a_lo or pi not in pa_prog.jit_attached or h not in pa_prog.free_positions(pi):
+                    if pi < a_lo or pi not in free_a or not all(h in free_a[pi] for h in hs):
                         break
                     pa.insert(0, pi)
                 pb: List[int] = []
                 for pi in b_rng:
-                    if pi not in pb_prog.jit_attached or h not in pb_prog.free_positions(pi):
+                    if pi not in free_b or not all(h in free_b[pi] for h in hs):
                         break
                     pb.append(pi)
-                score = sum(la.pass_bytes(pi) for pi in pa) + sum(lb.pass_bytes(pi) for pi in pb)
+                return pa, pb, sum(la.pass_bytes(pi) for pi in pa) + sum(lb.pass_bytes(pi) for pi in pb)
+
+            best = None
+            for h, ebit in cands:
+                pa, pb, score = runs([h])
                 if score > 0 and (best is None or score > best[0]):
-                    best = (score, h, ebit, pa, pb)
+                    best = (score, [h], [ebit], pa, pb)
+            if best is not None and max_pos > 1:
+                # a second position: quarters instead of halves (the exposed head and tail of the pipeline halve) if that
+                # keeps at least 3/4 of the overlapped passes
+                best2 = None
+                for i1, (h1, e1) in enumerate(cands):
+                    for h2, e2 in cands[i1 + 1:]:
+                        pa, pb, score = runs([h1, h2])
+                        if score > 0 and (best2 is None or score > best2[0]):
+                            best2 = (score, [h1, h2], [e1, e2], pa, pb)
+                if best2 is not None and 4 * best2[0] >= 3 * best[0]:
+                    best = best2
             if best is not None:
                 out[j] = best[1:]
                 used_prefix[j + 1] = (best[4][-1] + 1) if best[4] else 0
@@ -850,22 +890,23 @@ class ShardedShapedSolver:
             if j not in ov:
                 self.runner.swap_many(pairs)
                 continue
-            h, ebit, pa, pb = ov[j]
+            hs, ebits, pa, pb = ov[j]
             prog_a, prog_b = self.engine.programs[id(segs[j - 1].lowered)], self.engine.programs[id(segs[j + 1].lowered)]
             main = torch.cuda.current_stream()
-            _check(lib.qls_set_pass_grid_reserve(1))  # the exchange's barrier kernel needs an SM beside the persistent pass kernels
+            parts = [[(h, (part >> i) & 1) for i, h in enumerate(hs)] for part in range(1 << len(hs))]  # part i: bit j of i = value of hs[j]
+            _check(lib.qls_set_pass_grid_reserve(1))  # the exchange's sync kernels need an SM beside the persistent pass kernels
             try:
                 ready = []
-                for v in (0, 1):
+                for sel in parts:
                     for pi in pa:
-                        prog_a.run_pass_part(self.state, pi, h, v)
+                        prog_a.run_pass_part(self.state, pi, sel)
                     ready.append(main.record_event())
-                done = self.runner.exchange_ce(pairs, ready, half_bit=ebit)
-                for v in (0, 1):
-                    main.wait_event(done[v])
+                done = self.runner.exchange_ce(pairs, ready, part_bits=ebits)
+                for sel, ev in zip(parts, done):
+                    main.wait_event(ev)
                     for pi in pb:
-                        prog_b.run_pass_part(self.state, pi, h, v)
-                main.wait_event(done[1])
+                        prog_b.run_pass_part(self.state, pi, sel)
+                main.wait_event(done[-1])
             finally:
                 _check(lib.qls_set_pass_grid_reserve(0))
 
