@@ -278,6 +278,19 @@ def _plan_sharded(circuit: QuantumCircuit, world_size: int, opts: Optional[Lower
     return ShardedPlan(n, n_local, g, segments, initial, list(phys), amp_updates, len(leaves), deferred)
 
 
+def window_chunk_geometry(p: int, k: int, value: int, begin: int, count: int, esz: int) -> Tuple[int, int, int, int]:
+    """(byte offset in the shard, pitch, width, height -- all in bytes / rows) of elements ``[begin, begin + count)`` of the
+    sub-block whose local bits ``[p, p + k)`` equal ``value``: element ``e`` of the sub-block sits at amplitude index
+    ``(e >> p) << (p + k) | value << p | e & (2^p - 1)``, i.e. rows of ``2^p`` amplitudes at a pitch of ``2^(p+k)``.
+    ``begin`` and ``count`` are powers of two times each other (chunks of a power-of-two block)."""
+    row = 1 << p
+    if count <= row:  # inside one row
+        off = (((begin >> p) << (p + k)) | (value << p) | (begin & (row - 1))) * esz
+        return off, count * esz, count * esz, 1
+    off = (((begin >> p) << (p + k)) | (value << p)) * esz
+    return off, (row << k) * esz, row * esz, count >> p
+
+
 def solution_slice_plan(plan: ShardedPlan, nb: int, rank: int) -> Tuple[np.ndarray, np.ndarray, complex]:
     """Which entries of the solution slice (last qubit = 1, qubits nb..n-2 = 0, qubits 0..nb-1 = i) ``rank`` contributes to,
     their addresses in its shard, and the rank's weight (product of G[0][own bit] over the deferred gates G)."""
@@ -447,13 +460,7 @@ class ShardedRunner:
                         jobs.append((part, partner, value, b, min(chunk, block - b)))
 
         def geometry(value: int, begin: int, count: int) -> Tuple[int, int, int, int]:
-            """(byte offset in the state, pitch, width, height) of elements [begin, begin + count) of sub-block ``value``."""
-            row = 1 << p
-            if count <= row:  # inside one row
-                off = (((begin >> p) << (p + k)) | (value << p) | (begin & (row - 1))) * esz
-                return off, count * esz, count * esz, 1
-            off = (((begin >> p) << (p + k)) | (value << p)) * esz
-            return off, (row << k) * esz, row * esz, count >> p
+            return window_chunk_geometry(p, k, value, begin, count, esz)
 
         c1, c2 = eng.comm_stream, eng.scatter_stream
         pair_sync = os.environ.get("QLS_REMAP_PAIR_SYNC", "1") != "0" and self.world > 2

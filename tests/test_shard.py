@@ -275,3 +275,83 @@ def test_deferred_final_gates_fold_into_the_slice_reduction(world):
     half = 2 ** (n - 1)
     assert np.max(np.abs(x - want[half:half + 2**nb])) < 1e-12
     assert abs(p_flag - float(np.sum(np.abs(want[half:]) ** 2))) < 1e-12  # P(flag = 1) does not see a unitary on the clock
+
+
+def test_window_chunk_geometry_matches_the_gather_indices():
+    """The pitched-copy description of a chunk (copy-engine exchange of consecutive local positions) addresses exactly the
+    amplitudes the gather / scatter kernels' index deposit does."""
+    from qls_b200.shard import window_chunk_geometry
+
+    rng = np.random.default_rng(1)
+    n_local, esz = 14, 16
+    plan = plan_sharded(hhl_shaped_circuit(n_local + 1), 2, LoweringOptions(**OPTS), protect_low=2)
+    eng = NumpyShardEngine(plan, 0)
+    for _ in range(200):
+        k = int(rng.integers(1, 4))
+        p = int(rng.integers(0, n_local - k + 1))
+        value = int(rng.integers(0, 2**k))
+        block = 2 ** (n_local - k)
+        count = 2 ** int(rng.integers(0, n_local - k + 1))
+        begin = int(rng.integers(0, block // count)) * count
+        off, pitch, width, height = window_chunk_geometry(p, k, value, begin, count, esz)
+        got = np.concatenate([np.arange(width // esz) + (off + r * pitch) // esz for r in range(height)])
+        want = eng._block_index(list(range(p, p + k)), value, begin, count)
+        assert np.array_equal(got, want), (p, k, value, begin, count)
+
+
+@pytest.mark.parametrize("world,n,chunk_log2", [(2, 34, 27), (4, 35, 27), (8, 36, 27), (8, 29, 20), (2, 23, 15)])
+def test_overlap_plan_invariants(world, n, chunk_log2):
+    """Host-side dry run of ShardedShapedSolver._plan_overlap (stand-ins for the device objects): the split positions are
+    free in every overlapped pass and not exchanged, their element-index bits are at least log2(chunk), and the passes taken
+    before / after neighbouring exchanges do not overlap inside one segment."""
+    from qls_b200 import shard
+
+    class Prog:
+        def __init__(self, low):
+            self.lowered, self.jit_attached = low, set(range(low.n_passes))
+
+        def free_positions(self, i):
+            p = self.lowered.passes[i]
+            return [p.fseg[j].dst + w for j in range(p.n_fseg) for w in range(p.fseg[j].width)]
+
+    class Slot:
+        def numel(self):
+            return 1 << chunk_log2
+
+    class Runner:
+        chunk = 1 << chunk_log2
+
+        @staticmethod
+        def ce_capable(lposs):
+            ls = sorted(lposs)
+            return all(b - a == 1 for a, b in zip(ls, ls[1:]))
+
+    class Engine:
+        pass
+
+    plan = plan_sharded(hhl_shaped_circuit(n), world, LoweringOptions(dtype="fp64"), defer_final_1q=True)
+    solver = shard.ShardedShapedSolver.__new__(shard.ShardedShapedSolver)
+    eng = Engine()
+    eng.peers, eng._recv = {1: 1}, [Slot()]
+    eng.programs = {id(sg.lowered): Prog(sg.lowered) for sg in plan.segments if sg.kind == "local"}
+    solver.plan, solver.engine, solver.runner = plan, eng, Runner()
+    ov = solver._plan_overlap()
+    assert ov, "the HHL-shaped plans have exchanges of consecutive positions with free positions beside them"
+    taken = {}
+    for j, (hs, ebits, pa, pb) in ov.items():
+        seg = plan.segments[j]
+        lposs = sorted(l for _, l in seg.pairs)
+        assert 1 <= len(hs) <= 2 and len(set(hs)) == len(hs) and not set(hs) & set(lposs)
+        for h, e in zip(hs, ebits):
+            assert e == h - sum(1 for l in lposs if l < h) and (1 << e) >= (1 << chunk_log2)
+        pa_prog, pb_prog = eng.programs[id(plan.segments[j - 1].lowered)], eng.programs[id(plan.segments[j + 1].lowered)]
+        assert all(set(hs) <= set(pa_prog.free_positions(i)) for i in pa)
+        assert all(set(hs) <= set(pb_prog.free_positions(i)) for i in pb)
+        n_a = plan.segments[j - 1].lowered.n_passes
+        assert pa == list(range(n_a - len(pa), n_a)) and pb == list(range(len(pb)))  # a suffix / a prefix
+        for i in pa:
+            assert (j - 1, i) not in taken
+            taken[(j - 1, i)] = j
+        for i in pb:
+            assert (j + 1, i) not in taken
+            taken[(j + 1, i)] = j
