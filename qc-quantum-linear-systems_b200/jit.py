@@ -478,8 +478,9 @@ class _Gen:
             for r in todo:
                 by_idx.setdefault(rt[r], []).append(r)
             keys = list(by_idx)
-            for c in range(0, len(keys), 4):  # four phases in flight
-                chunk = keys[c:c + 4]
+            nb_ = int(os.environ.get("QLS_JIT_DIAG_BATCH", "4"))
+            for c in range(0, len(keys), nb_):  # four phases in flight (eight measured: see profiles/README.md)
+                chunk = keys[c:c + nb_]
                 for n, key in enumerate(chunk):
                     self.emit(f"const V p{c + n} = __ldg(tab + {key});", ind)
                 for n, key in enumerate(chunk):
@@ -493,8 +494,9 @@ class _Gen:
                 i0 = ((g >> q) << (q + 1)) | (g & ((1 << q) - 1))
                 if (i0 & rm) == rv:
                     pairs.append(i0)
-            for c in range(0, len(pairs), 4):
-                chunk = pairs[c:c + 4]
+            nb_ = int(os.environ.get("QLS_JIT_DIAG_BATCH", "4"))
+            for c in range(0, len(pairs), nb_):
+                chunk = pairs[c:c + nb_]
                 for n, i0 in enumerate(chunk):
                     self.emit(f"const V p{c + n} = __ldg(tab + {rt[i0]});", ind)
                 for n, i0 in enumerate(chunk):
