@@ -467,19 +467,22 @@ class LoweredProgram:
         """Real fused multiply-adds of the register-stage form (complex 4x4: 16 per amplitude, real
         4x4: 8, complex 2x2: 8, real 2x2: 4, table lookups: 4), halved per control.  Passes without a
         register-stage form are not counted."""
+        return sum(self.pass_fma_count(i, n_local) for i in range(self.n_passes))
+
+    def pass_fma_count(self, i: int, n_local: Optional[int] = None) -> float:
+        """Real fused multiply-adds of pass ``i`` (register-stage form; see ``fp64_fma_count``)."""
         n = self.n_local if n_local is None else n_local
         per = {_abi.QLS_RS_G1: (8, 4), _abi.QLS_RS_G2: (16, 8), _abi.QLS_RS_DIAG: (4, 4), _abi.QLS_RS_MUXRY: (4, 4)}
         tot = 0.0
-        for i in range(self.n_passes):
-            p = self.passes[i]
-            for o in range(p.rs_begin, p.rs_begin + p.rs_count):
-                op = self.rs_ops[o]
-                if op.kind not in per:
-                    continue
-                c = per[op.kind][1 if (op.flags & _abi.QLS_OP_FLAG_REAL) else 0]
-                # controls outside the tile and the pass-level fixed bits (shared controls, qubits still |0>) restrict the tiles
-                nc = bin(op.xc_mask | p.fix_mask).count("1") + bin(op.ctl_tmask).count("1") + bin(op.ctl_rmask).count("1")
-                tot += c * 0.5**nc * 2.0**n
+        p = self.passes[i]
+        for o in range(p.rs_begin, p.rs_begin + p.rs_count):
+            op = self.rs_ops[o]
+            if op.kind not in per:
+                continue
+            c = per[op.kind][1 if (op.flags & _abi.QLS_OP_FLAG_REAL) else 0]
+            # controls outside the tile and the pass-level fixed bits (shared controls, qubits still |0>) restrict the tiles
+            nc = bin(op.xc_mask | p.fix_mask).count("1") + bin(op.ctl_tmask).count("1") + bin(op.ctl_rmask).count("1")
+            tot += c * 0.5**nc * 2.0**n
         return tot
 
     def amp_updates(self) -> int:
