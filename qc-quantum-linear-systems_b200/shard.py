@@ -901,7 +901,8 @@ class ShardedShapedSolver:
             prog_a, prog_b = self.engine.programs[id(segs[j - 1].lowered)], self.engine.programs[id(segs[j + 1].lowered)]
             main = torch.cuda.current_stream()
             parts = [[(h, (part >> i) & 1) for i, h in enumerate(hs)] for part in range(1 << len(hs))]  # part i: bit j of i = value of hs[j]
-            _check(lib.qls_set_pass_grid_reserve(1))  # the exchange's sync kernels need an SM beside the persistent pass kernels
+            # the exchange's hand-shake kernels (NCCL, one or two CTAs) need SMs beside the persistent pass kernels
+            _check(lib.qls_set_pass_grid_reserve(int(os.environ.get("QLS_SHARD_OVERLAP_SMS", "2"))))
             try:
                 ready = []
                 for sel in parts:
