@@ -143,3 +143,26 @@ def test_batched_program_with_wide_operator_uses_matvec():
     got = run_program(low, params=theta)
     want = numpy_sv.run(nq + 1, circuit_to_stream(test.circuits[1].assign_parameters(theta)))
     assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_batched_lowering_uses_still_zero_qubits():
+    """Batched circuits start from |0...0>: a block that does not use a qubit nothing has acted on yet skips the amplitudes
+    with that bit set (a control on value 0), and a block controlled on such a qubit is the identity and is dropped.  Same
+    state as bind + oracle."""
+    rng = np.random.default_rng(9)
+    qc = QuantumCircuit(5)
+    qc.ry(0.3, 1)
+    qc.cx(4, 2)            # control qubit 4 is still |0>: dropped
+    qc.cx(1, 2)
+    qc.unitary(random_unitary(2, rng), [1, 3])
+    qc.h(0)                # the ancilla wakes up last
+    qc.cx(0, 4)
+    low = lower_circuit(qc, LoweringOptions(batch=True, max_fuse_qubits=1))
+    ops = [low.ops[i] for i in range(low.pass_info[0].n_ops)]
+    assert len(ops) == 5                                          # cx(4, 2) is gone
+    assert ops[0].lc_mask == 0b11101 and ops[0].lc_val == 0        # ry on qubit 1: every other qubit is still |0>
+    assert ops[1].lc_mask & 0b10001 == 0b10001 and (ops[1].lc_val & 0b10001) == 0  # cx(1, 2): qubits 0 and 4 still |0>
+    assert ops[-1].lc_mask == 0b00001 and ops[-1].lc_val == 1      # cx(0, 4): only its real control is left
+    got = run_program(low)
+    want = numpy_sv.run(5, circuit_to_stream(qc))
+    assert np.max(np.abs(got - want)) < 1e-14
