@@ -125,3 +125,33 @@ __device__ __forceinline__ void cp_async_wait() {
 // in place on the FP64 tensor pipe (ctrl_gemm.cu; 6 <= nb <= 10)
 int qls_gemm_rows_inplace(void* state, uint64_t total_rows, int nb, uint64_t row_mask, uint64_t row_val, const void* u_dev,
                           cudaStream_t stream);
+
+// A __constant__ image that is refreshed before every launch (register-stage pass description, wide dense matrices of the sweep
+// kernel) exists once per device: two launches that use it must not overlap.  Launches on ONE stream are ordered anyway; a
+// launch on another stream first waits for the previous user (event recorded after it), so the constraint is enforced here
+// instead of being left to the caller.  Call `before` ahead of the cudaMemcpyToSymbolAsync and `after` behind the kernel launch.
+struct QlsConstGuard {
+  cudaEvent_t ev[64] = {};
+  cudaStream_t last[64] = {};
+  bool used[64] = {};
+  int before(int device, cudaStream_t s) {
+    const int d = device & 63;
+    if (used[d] && last[d] != s) {
+      cudaError_t e = cudaStreamWaitEvent(s, ev[d], 0);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+  }
+  int after(int device, cudaStream_t s) {
+    const int d = device & 63;
+    if (!ev[d]) {
+      cudaError_t e = cudaEventCreateWithFlags(&ev[d], cudaEventDisableTiming);
+      if (e != cudaSuccess) return (int)e;
+    }
+    cudaError_t e = cudaEventRecord(ev[d], s);
+    if (e != cudaSuccess) return (int)e;
+    used[d] = true;
+    last[d] = s;
+    return 0;
+  }
+};

@@ -92,6 +92,7 @@ struct RsImage {
 };
 
 __constant__ RsImage c_img;
+static QlsConstGuard g_img_guard;  // every instantiation of the kernel reads the one image of its device
 
 // swizzle of a tile-local amplitude index; SH = log2(amplitudes per 16-byte unit)
 template <int SH>
@@ -608,7 +609,9 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
     QLS_CUDA(cudaDeviceGetAttribute(&sm_count[prog->device & 63], cudaDevAttrMultiProcessorCount, prog->device));
     attr_set[prog->device & 63] = true;
   }
-  // the pass description goes to constant memory; stream order keeps it alive for exactly this launch
+  // the pass description goes to constant memory; stream order keeps it alive for exactly this launch (and a launch on another
+  // stream of the same device waits for this one: QlsConstGuard)
+  QLS_ARG(g_img_guard.before(prog->device, stream) == 0, "stream wait on the previous user of the pass image failed");
   QLS_CUDA(cudaMemcpyToSymbolAsync(c_img, prog->rs_img_dev + prog->rs_img_off[pass_index], prog->rs_img_bytes[pass_index], 0,
                                    cudaMemcpyDeviceToDevice, stream));
   uint64_t grid = (uint64_t)CTAS * (uint64_t)sm_count[prog->device & 63];
@@ -617,6 +620,7 @@ int launch_rs(const QlsProgram* prog, const QlsPass& p, uint32_t pass_index, voi
   kern<<<(unsigned)grid, GROUPS * RS_THREADS, smem, stream>>>(reinterpret_cast<V*>(state), index_offset, n_tiles, prog->pool_dev,
                                                      dbg_env ? (uint32_t)atoi(dbg_env) : 0u);
   QLS_CUDA(cudaGetLastError());
+  QLS_ARG(g_img_guard.after(prog->device, stream) == 0, "event record behind the pass kernel failed");
   return QLS_OK;
 }
 

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(THREADS, HEAVY ? 2 : 3)
 
 // ---- host side --------------------------------------------------------------------------------------
 
+static QlsConstGuard g_heavy_guard;  // one c_heavy table per device: launches that use it never overlap
+
 template <typename R, bool HEAVY>
 static int launch_pass(const QlsProgram* prog, const QlsPass& p, void* state, int n_local, uint64_t index_offset,
                        cudaStream_t stream) {
@@ -95,7 +97,10 @@ static int launch_pass(const QlsProgram* prog, const QlsPass& p, void* state, in
   tl.index_offset = index_offset;
   tl.n_ops = p.op_count;
   for (int j = 0; j < QLS_MAX_HEAVY; ++j) tl.heavy_off[j] = 0xFFFFu;
+  bool uses_const = false;
   if (HEAVY && sizeof(V) == 16) {
+    QLS_ARG(g_heavy_guard.before(prog->device, stream) == 0, "stream wait on the previous user of the matrix table failed");
+    uses_const = true;
     // matrices of the wide dense blocks -> __constant__ table (device to device, stream ordered)
     uint32_t used = 0;
     int seen = 0;
@@ -125,6 +130,7 @@ static int launch_pass(const QlsProgram* prog, const QlsPass& p, void* state, in
   const unsigned grid = 1u << free_bits;
   kern<<<grid, THREADS, smem, stream>>>(reinterpret_cast<V*>(state), tl, prog->ops_dev + p.op_begin, prog->pool_dev);
   QLS_CUDA(cudaGetLastError());
+  if (uses_const) QLS_ARG(g_heavy_guard.after(prog->device, stream) == 0, "event record behind the pass kernel failed");
   return QLS_OK;
 }
 
