@@ -74,7 +74,9 @@ class ShapedSolver:
 
     def reduce(self) -> Tuple[float, float]:
         half = 2 ** (self.n - 1)
-        p_flag = self.state.prob_mask(half, half)
+        # the flag is the top qubit: P(flag = 1) is the norm of the upper half -- a range reduction reads 64 GiB of a
+        # 33-qubit state, the masked one (every amplitude, test the bit) all 128
+        p_flag = self.state.norm_sq_range(half, half)
         norm_sq = self.state.norm_sq_range(half, 2**self.nb)
         return p_flag, norm_sq
 
