@@ -226,7 +226,9 @@ int qls_ctrl_gemm(void* state, void* scratch, int n_local, int dtype, int nb, ui
 /* ---- batch of small circuits (VQLS Hadamard tests) ----------------------------------------- */
 
 /* K circuits of n_qubits (<= 12) sharing one op program; ops flagged as parameterised take their
- * angle from params_dev[circuit*P + index].  out_dev[circuit] = <Z_qubit>.
+ * angle from params_dev[circuit*P + index].  out_dev[circuit] = <Z_qubit>.  Programs with a dense operator on 6..10
+ * qubits keep a launch-wide state array (<= 512 MiB) inside the program object: launches of ONE program must be stream
+ * ordered with one another (different programs are independent).
  * [Estimator.run(circuits, observables, parameter_values), vqls..:55-62] */
 int qls_batch_expect_z(const QlsProgram* prog, uint32_t pass_index, int n_qubits, int z_qubit, const double* params_dev,
                        uint32_t n_circuits, uint32_t n_params, double* out_dev, void* stream);

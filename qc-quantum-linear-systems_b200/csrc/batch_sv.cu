@@ -290,7 +290,18 @@ static int batch_expect_z_gemm(const QlsProgram* prog, const QlsPass& p, int n, 
   uint32_t chunk = (uint32_t)(((size_t)512 << 20) / ((size_t)16 << n));
   if (chunk > n_circuits) chunk = n_circuits;
   double2* scratch = nullptr;
-  if (p.pad & 2u) QLS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), ((size_t)16 << n) * chunk, s));
+  if (p.pad & 2u) {
+    const uint64_t need = ((uint64_t)16 << n) * chunk;
+    QlsProgram* mp = const_cast<QlsProgram*>(prog);  // the scratch array is a cache of the program object
+    if (mp->batch_scratch_bytes < need) {
+      if (mp->batch_scratch) QLS_CUDA(cudaFree(mp->batch_scratch));  // (synchronises: earlier launches are done with it)
+      mp->batch_scratch = nullptr;
+      mp->batch_scratch_bytes = 0;
+      QLS_CUDA(cudaMalloc(&mp->batch_scratch, need));
+      mp->batch_scratch_bytes = need;
+    }
+    scratch = reinterpret_cast<double2*>(mp->batch_scratch);
+  }
   int rc = QLS_OK;
   for (uint32_t c0 = 0; c0 < n_circuits && rc == QLS_OK; c0 += chunk) {
     const uint32_t nc = n_circuits - c0 < chunk ? n_circuits - c0 : chunk;
@@ -320,7 +331,6 @@ static int batch_expect_z_gemm(const QlsProgram* prog, const QlsPass& p, int n, 
       }
     }
   }
-  if (scratch) cudaFreeAsync(scratch, s);
   if (rc != QLS_OK) return rc;
   QLS_CUDA(cudaGetLastError());
   return QLS_OK;

@@ -47,6 +47,10 @@ struct QlsProgram {
   uint8_t* rs_img_kr;      // [n_passes] register qubits per thread of the pass's stages (4 or 5)
   // specialised (NVRTC-compiled) kernels, one per pass that has one; nullptr: none attached (jit.cu)
   struct QlsJitKernel** jit;
+  // launch-wide state array of the batched estimator's GEMM form (batch_sv.cu): allocated on first use, grown on demand,
+  // freed with the program (a stream-ordered allocation per call cost up to 4 ms per launch when the pool had been trimmed)
+  void* batch_scratch;
+  uint64_t batch_scratch_bytes;
 };
 
 // register-stage fast path (rs_pass.cu)

@@ -264,6 +264,8 @@ extern "C" int qls_program_create(const QlsPass* passes_host, uint32_t n_passes,
   p->rs_img_bytes = nullptr;
   p->rs_img_kr = nullptr;
   p->jit = nullptr;
+  p->batch_scratch = nullptr;
+  p->batch_scratch_bytes = 0;
   for (uint32_t i = 0; i < n_passes; ++i) {
     p->passes_host[i] = passes_host[i];
     QlsPass& ps = p->passes_host[i];
@@ -343,6 +345,7 @@ extern "C" int qls_program_destroy(QlsProgram* prog) {
   if (prog->rs_ops_dev) cudaFree(prog->rs_ops_dev);
   if (prog->pool_dev) cudaFree(prog->pool_dev);
   if (prog->rs_img_dev) cudaFree(prog->rs_img_dev);
+  if (prog->batch_scratch) cudaFree(prog->batch_scratch);
   qls_jit_release(prog);
   delete[] prog->rs_img_off;
   delete[] prog->rs_img_bytes;
